@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Generate ``tests/golden/*.npz`` by running the REAL reference code on seeded inputs.
+
+TEST INFRASTRUCTURE.  Runs only where the reference checkout exists (the build container,
+``/root/reference``); the fixtures it writes are committed so that nothing on the GPU box ever
+needs the checkout.  Re-run with:  ``python -m oracle.gen_golden [--ref /root/reference]``.
+
+What is executed from the reference (never copied into this repo):
+  * imported as modules: ``local_utils/faster_mix_k_means_pytorch.py`` (K_Means, pairwise_distance),
+    ``gcd/methods/clustering/faster_mix_k_means_pytorch.py`` (the copy the drivers import; ``mode=``),
+    ``local_utils/clip_lang_util.py`` (assign_name, accuracy) and through it
+    ``gcd/project_utils/cluster_utils.py`` (linear_assignment).  Import-time-only dependencies that
+    are not installed (nltk, clip, matplotlib, seaborn, sklearn.utils._joblib) are stubbed.
+  * exec'd from their source text, because they are inline script code under ``__main__``:
+    ``main_unsup.py`` scoring block (TOP_K ... torch.cat) and voting loop (while ... argmax),
+    ``main_ptsup.py`` scoring block and voting loop.  The line ranges are located by sentinel
+    strings and the text is dedented and executed in a namespace holding the synthetic inputs.
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import os
+import sys
+import textwrap
+import types
+from collections import Counter
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+OUT = os.path.join(REPO, 'tests', 'golden')
+
+
+# ------------------------------------------------------------------ reference import plumbing
+def _stub(name, **attrs):
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+    sys.modules[name] = mod
+    return mod
+
+
+def import_reference(ref):
+    import joblib
+    _stub('nltk')
+    _stub('nltk.corpus', wordnet=None)
+    _stub('clip')
+    plt = _stub('matplotlib.pyplot', get=None)
+    _stub('matplotlib', pyplot=plt, use=lambda *a, **k: None)
+    _stub('seaborn')
+    _stub('sklearn.utils._joblib', Parallel=joblib.Parallel, delayed=joblib.delayed,
+          effective_n_jobs=joblib.effective_n_jobs)
+    for p in (ref, os.path.join(ref, 'gcd'), os.path.join(ref, 'local_utils')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import warnings
+    warnings.simplefilter('ignore')
+    import importlib
+    km_local = importlib.import_module('local_utils.faster_mix_k_means_pytorch')
+    km_gcd = importlib.import_module('gcd.methods.clustering.faster_mix_k_means_pytorch')
+    lang = importlib.import_module('local_utils.clip_lang_util')
+    cu = importlib.import_module('gcd.project_utils.cluster_utils')
+    return km_local, km_gcd, lang, cu
+
+
+def source_block(path, first_sentinel, last_sentinel, after=None):
+    """Return the dedented text from the line containing ``first_sentinel`` (searched after the line
+    containing ``after``, if given) through the line containing ``last_sentinel``, plus its 1-based range."""
+    with open(path) as f:
+        lines = f.readlines()
+    start = 0
+    if after is not None:
+        start = next(i for i, l in enumerate(lines) if after in l) + 1
+    a = next(i for i in range(start, len(lines)) if first_sentinel in lines[i])
+    b = next(i for i in range(a, len(lines)) if last_sentinel in lines[i])
+    return textwrap.dedent(''.join(lines[a:b + 1])), (a + 1, b + 1)
+
+
+# ------------------------------------------------------------------ synthetic inputs
+def unit_rows(x):
+    return x / x.norm(dim=1, keepdim=True)
+
+
+def clustered_feats(n, d, k_true, seed, spread=4.0):
+    g = torch.Generator().manual_seed(seed)
+    mu = unit_rows(torch.randn(k_true, d, generator=g))
+    y = torch.randint(0, k_true, (n,), generator=g)
+    x = unit_rows(torch.randn(n, d, generator=g) + spread * mu[y])
+    return x.float().contiguous(), y
+
+
+def bf16_round(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+# ------------------------------------------------------------------ k-means fixtures
+def gen_kmeans(km_local, km_gcd):
+    from sklearn.datasets import make_blobs
+    # (1) the reference's own demo, local_utils/faster_mix_k_means_pytorch.py:221-249 (float64 inputs!)
+    X, y = make_blobs(n_samples=500, n_features=2, centers=4, cluster_std=1, center_box=(-10.0, 10.0),
+                      shuffle=True, random_state=1)
+    l_t, l_f, u_f = y[y > 1], X[y > 1], X[y < 2]
+    km = km_local.K_Means(k=4, init='k-means++', random_state=1, n_jobs=None, pairwise_batch_size=10)
+    km.fit_mix(torch.from_numpy(u_f), torch.from_numpy(l_f), torch.from_numpy(l_t))
+    np.savez_compressed(os.path.join(OUT, 'kmeans_blobs_demo.npz'),
+                        u_feats=u_f, l_feats=l_f, l_targets=l_t,
+                        labels=km.labels_.numpy(), centers=km.cluster_centers_.numpy(),
+                        inertia=np.float64(km.inertia_.item()), n_iter=np.int64(km.n_iter_))
+
+    # (2) DINO-like unit-norm fp32 features, semi-supervised, both class copies, k-means++ and random
+    n, d, k = 600, 64, 12
+    X, y = clustered_feats(n, d, k, seed=11)
+    lab = (y < k // 2) & (torch.rand(n, generator=torch.Generator().manual_seed(12)) < 0.5)
+    l_f, u_f = X[lab].contiguous(), X[~lab].contiguous()
+    l_t = y[lab].double()                                   # drivers pass float64 targets (main_unsup.py:118,132)
+    C0 = X[:k].clone()
+    out = dict(u_feats=u_f.numpy(), l_feats=l_f.numpy(), l_targets=l_t.numpy(), X=X.numpy(), C0=C0.numpy())
+    out['pd_none'] = km_local.pairwise_distance(X, C0, None).numpy()
+    out['pd_b100'] = km_local.pairwise_distance(X, C0, 100).numpy()
+    out['pd_b600'] = km_local.pairwise_distance(X, C0, 600).numpy()
+    for tag, mod, extra in (('local', km_local, {}), ('gcd', km_gcd, {'mode': None})):
+        km = mod.K_Means(k=k, tolerance=1e-4, max_iterations=10, init='k-means++', n_init=2,
+                         random_state=7, n_jobs=None, pairwise_batch_size=128, **extra)
+        km.fit_mix(u_f, l_f, l_t)
+        out[f'mix_{tag}_labels'] = km.labels_.numpy()
+        out[f'mix_{tag}_centers'] = km.cluster_centers_.numpy()
+        out[f'mix_{tag}_inertia'] = np.float64(km.inertia_.item())
+        out[f'mix_{tag}_n_iter'] = np.int64(km.n_iter_)
+    for init in ('random', 'first', 'k-means++'):
+        km = km_local.K_Means(k=k, tolerance=1e-4, max_iterations=6, init=init, n_init=2,
+                              random_state=3, n_jobs=None, pairwise_batch_size=None)
+        km.fit(X)
+        tag = init.replace('-', '').replace('+', 'p')
+        out[f'fit_{tag}_labels'] = km.labels_.numpy()
+        out[f'fit_{tag}_centers'] = km.cluster_centers_.numpy()
+        out[f'fit_{tag}_inertia'] = np.float64(km.inertia_.item())
+        out[f'fit_{tag}_n_iter'] = np.int64(km.n_iter_)
+    # kpp seed selection alone (host RNG stream + cumsum threshold)
+    km = km_local.K_Means(k=k, pairwise_batch_size=None)
+    out['kpp_centers'] = km.kpp(X, k=k, random_state=5).numpy()
+    out['kpp_pre_centers'] = km.kpp(u_f, pre_centers=X[:3].clone(), k=k, random_state=5).numpy()
+    np.savez_compressed(os.path.join(OUT, 'kmeans_small.npz'), **out)
+
+    # (3) empty cluster -> NaN centroid (duplicate first rows with the 'first k rows' init); one iteration
+    Xd = X[:200].clone()
+    Xd[1] = Xd[0]
+    km = km_local.K_Means(k=5, max_iterations=1, init='first', n_init=1, random_state=0, pairwise_batch_size=None)
+    km.fit(Xd)
+    np.savez_compressed(os.path.join(OUT, 'kmeans_empty_cluster.npz'), X=Xd.numpy(),
+                        labels=km.labels_.numpy(), centers=km.cluster_centers_.numpy(),
+                        inertia=np.float64(km.inertia_.item()))
+
+
+# ------------------------------------------------------------------ Hungarian fixtures
+def gen_hungarian(cu):
+    rng = np.random.RandomState(0)
+    out = {}
+    shapes = [(1, 1), (2, 2), (3, 3), (5, 5), (8, 8), (13, 13), (20, 20), (33, 33), (40, 40), (4, 7), (7, 4), (12, 30)]
+    for i, (r, c) in enumerate(shapes):
+        for j, hi in enumerate((3, 50)):                  # hi=3 -> massively tied costs
+            cost = rng.randint(0, hi, size=(r, c))
+            out[f'cost_{i}_{j}'] = cost
+            out[f'ind_{i}_{j}'] = cu.linear_assignment(cost.copy())
+    np.savez_compressed(os.path.join(OUT, 'hungarian.npz'), **out)
+
+
+# ------------------------------------------------------------------ naming fixtures
+class _Args:
+    pass
+
+
+def gen_naming(ref, lang):
+    d, v, k_true = 32, 300, 10
+    res = {}
+    unsup_src = os.path.join(ref, 'main_unsup.py')
+    ptsup_src = os.path.join(ref, 'main_ptsup.py')
+
+    score_unsup, r1 = source_block(unsup_src, 'TOP_K = args.topk', 'name_logits_top5 = torch.cat')
+    score_ptsup, r2 = source_block(ptsup_src, 'TOP_K = 5', 'name_logits_top5 = torch.cat',
+                                   after='## obtain top 5 predictions by CLIP')
+    loop_unsup, r3 = source_block(unsup_src, 'while (set(cur_voted_names)', 'u_preds = logits.argmax')
+    loop_ptsup, r4 = source_block(ptsup_src, 'while (set(cur_voted_names)', 'u_preds = logits.argmax')
+    res['ranges'] = np.array([r1, r2, r3, r4])
+    print('exec ranges: unsup score %s, ptsup score %s, unsup loop %s, ptsup loop %s' % (r1, r2, r3, r4))
+
+    g = torch.Generator().manual_seed(21)
+    W = bf16_round(unit_rows(torch.randn(v, d, generator=g))).t().contiguous()       # [D,V], V-contiguous
+    res['W'] = W.numpy()
+    for n in (700, 2048, 2500):              # < one batch, exact multiple (empty trailing batch), ragged
+        feats, y = clustered_feats(n, d, k_true, seed=100 + n)
+        feats = bf16_round(feats)
+        args = _Args()
+        args.topk = 5
+        ns = dict(args=args, clip_all_feats=feats, zeroshot_weights=W, torch=torch, F=F, tqdm=lambda x: x)
+        exec(score_unsup, ns)
+        res[f'feats_{n}'] = feats.numpy()
+        res[f'unsup_idx_{n}'] = ns['name_idx_top5'].numpy()
+        res[f'unsup_val_{n}'] = ns['name_logits_top5'].numpy()
+        ns = dict(clip_all_feats=feats, zeroshot_weights=W, torch=torch, F=F, tqdm=lambda x: x)
+        exec(score_ptsup, ns)
+        res[f'ptsup_idx_{n}'] = ns['name_idx_top5'].numpy()
+        res[f'ptsup_val_{n}'] = ns['name_logits_top5'].numpy()
+        # accuracy() on full logits of the first 512 rows against synthetic targets
+        logits = 100. * feats[:512] @ W
+        tgt = torch.randint(0, v, (512,), generator=torch.Generator().manual_seed(n))
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            res[f'acc_{n}'] = np.array(lang.accuracy(logits, tgt, topk=(1, 5)))
+        res[f'acc_tgt_{n}'] = tgt.numpy()
+
+    # ---- voting loops on n = 2500 (names are ints: nouns[i] == i, so set/sort order is hash-seed free)
+    n = 2500
+    feats = torch.from_numpy(res[f'feats_{n}'])
+    idx_top = torch.from_numpy(res[f'ptsup_idx_{n}'])
+    _, y = clustered_feats(n, d, k_true, seed=100 + n)
+    g2 = torch.Generator().manual_seed(5)
+    noise = torch.randint(0, k_true, (n,), generator=g2)
+    flip = torch.rand(n, generator=g2) < 0.15
+    preds0 = torch.where(flip, noise, y).numpy().astype(np.int64)        # imperfect clustering result
+    nouns = list(range(v))
+    rec = []
+
+    def fake_split_acc(y_true, y_pred, mask, return_ind_map=False):
+        rec.append(np.array(y_pred).copy())
+        return (0., 0., 0., {}) if return_ind_map else (0., 0., 0.)
+
+    args = _Args()
+    args.num_common_vote, args.num_common_linear, args.n_cluster, args.dataset_name = 20, 4, k_true, 'cub'
+    voted = []
+
+    def fake_sem_acc(t, c2n, p, cand_names):
+        if not voted or voted[-1] is not cand_names:
+            voted.append(cand_names)
+        return 0., 0.
+
+    ns = dict(args=args, name_idx_top5=idx_top, u_preds=preds0.copy(), nouns=nouns, zeroshot_weights=W,
+              clip_u_feats=feats, num_unlab_classes=k_true, cur_voted_names=[0.5], prev_voted_names=[1.5],
+              top_k=5, it=0, Counter=Counter, copy=copy, torch=torch, assign_name=lang.assign_name,
+              split_cluster_acc_v2=fake_split_acc, evaluate_semantic_acc=fake_sem_acc,
+              u_targets=None, mask=None, cidx_to_cname=None, print=lambda *a, **k: None)
+    # the exec'd text ends at the argmax line; the metric calls after it are outside the block, so
+    # run the block round by round: it is a ``while`` loop -> wrap to record each round.
+    loop_body_unsup = loop_unsup.replace('u_preds = logits.argmax(dim=-1).view(-1).cpu().numpy()',
+                                         'u_preds = logits.argmax(dim=-1).view(-1).cpu().numpy()\n'
+                                         '    _rec(cur_voted_names, u_preds, len(voted_unique_name_idx))')
+    trace = []
+    ns['_rec'] = lambda names, p, nu: trace.append((list(names), np.array(p).copy(), nu))
+    exec(loop_body_unsup, ns)
+    res['unsup_loop_preds0'] = preds0
+    res['unsup_loop_rounds'] = np.int64(len(trace))
+    for r, (names, p, nu) in enumerate(trace):
+        res[f'unsup_loop_voted_{r}'] = np.array(names, dtype=np.int64)
+        res[f'unsup_loop_preds_{r}'] = p.astype(np.int64)
+        res[f'unsup_loop_nuniq_{r}'] = np.int64(nu)
+
+    # ptsup: first k_true//2 classes are labelled; labelled rows get their class as cluster id
+    mask_lab = ((y < k_true // 2) & (torch.rand(n, generator=torch.Generator().manual_seed(6)) < 0.5)).numpy()
+    all_preds = preds0.copy()
+    all_preds[mask_lab] = y.numpy()[mask_lab]
+    lab_names = [int(idx_top[(y == c).numpy() & mask_lab][:, 0].mode().values) for c in range(k_true // 2)]
+    lab_names = list(dict.fromkeys(lab_names))                 # distinct, order kept
+    u_preds = all_preds[~mask_lab]
+    l_preds = all_preds[mask_lab]
+    trace = []
+    ns = dict(args=args, name_idx_top5=idx_top[~mask_lab], u_preds=u_preds.copy(), nouns=nouns,
+              zeroshot_weights=W, clip_u_feats=feats[~mask_lab], lab_names=lab_names,
+              num_unlab_classes=k_true - len(lab_names), known_name_idx=[nouns.index(x) for x in lab_names],
+              unlab_cluster_idx=list(set(list(set(all_preds))) - set(list(set(l_preds)))),
+              cur_voted_names=[0.5], prev_voted_names=[1.5], top_k=5, it=0, Counter=Counter, copy=copy,
+              torch=torch, assign_name=lang.assign_name, print=lambda *a, **k: None,
+              _rec=lambda names, cand, p, nu: trace.append((list(names), list(cand), np.array(p).copy(), nu)))
+    loop_body_ptsup = loop_ptsup.replace('u_preds = logits.argmax(dim=-1).view(-1).cpu().numpy()',
+                                         'u_preds = logits.argmax(dim=-1).view(-1).cpu().numpy()\n'
+                                         '    _rec(cur_voted_names, cand_names, u_preds, len(voted_unique_name_idx))')
+    exec(loop_body_ptsup, ns)
+    res['ptsup_loop_all_preds'] = all_preds
+    res['ptsup_loop_mask_lab'] = mask_lab
+    res['ptsup_loop_lab_names'] = np.array(lab_names, dtype=np.int64)
+    res['ptsup_loop_rounds'] = np.int64(len(trace))
+    for r, (names, cand, p, nu) in enumerate(trace):
+        res[f'ptsup_loop_voted_{r}'] = np.array(names, dtype=np.int64)
+        res[f'ptsup_loop_cand_{r}'] = np.array(cand, dtype=np.int64)
+        res[f'ptsup_loop_preds_{r}'] = p.astype(np.int64)
+        res[f'ptsup_loop_nuniq_{r}'] = np.int64(nu)
+    np.savez_compressed(os.path.join(OUT, 'naming_small.npz'), **res)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--ref', default='/root/reference')
+    a = ap.parse_args()
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)          # fixtures must not depend on the thread count of this box
+    km_local, km_gcd, lang, cu = import_reference(a.ref)
+    gen_kmeans(km_local, km_gcd)
+    gen_hungarian(cu)
+    gen_naming(a.ref, lang)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == '__main__':
+    main()
