@@ -1,0 +1,119 @@
+/*
+ * scd_b200 - C ABI of the B200-native clustering-and-naming hot path of Visual-AI/SCD.
+ *
+ * The reference has no FFI: its hot path is plain PyTorch calls inside two Python classes and two
+ * driver scripts.  Each entry point below therefore cites the reference *call site(s)* whose device
+ * work it replaces (paths relative to the reference checkout).  The Python layer in scd_b200/
+ * keeps the reference's class / function signatures and calls these through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors kept alive by the host
+ *     layer) unless it says "host"; no function allocates; scratch comes in through (ws, ws_bytes)
+ *     sized by the matching *_workspace_bytes();
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work, they never synchronise;
+ *   - return 0 on success, non-zero on error with a message in scd_last_error() (thread local);
+ *   - matrices are row-major and dense unless a leading dimension is given.
+ */
+#ifndef SCD_B200_H_
+#define SCD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SCD_API __attribute__((visibility("default")))
+#else
+#define SCD_API
+#endif
+
+typedef void* scd_stream_t;      /* cudaStream_t */
+typedef uint16_t scd_bf16_t;     /* raw bfloat16 bits */
+
+SCD_API int scd_version(void);
+SCD_API const char* scd_last_error(void);
+
+/* ---------------------------------------------------------------- k-means (a1-a4) */
+
+/* local_utils/faster_mix_k_means_pytorch.py:177-212 pairwise_distance (copies: sskm_constrained.py:189,
+ * gcd/methods/clustering/faster_mix_k_means_pytorch.py:9): out[n,k] = sum_d (X[n,d]-C[k,d])^2, direct form, fp32.
+ * cost_x1000 (nullable, [N,K] int32) = round(1000*sqrt(out)): local_utils/sskm_constrained.py:116 + :324. */
+SCD_API int scd_pairwise_distance(const float* X, int64_t N, int D, const float* C, int K,
+                          float* out /* nullable */, int32_t* cost_x1000 /* nullable */, scd_stream_t stream);
+
+/* E-step, faster_mix_k_means_pytorch.py:58-60 / :105-107: labels = argmin_k dist (ties -> lowest k, NaN wins),
+ * mindist = min_k dist, *inertia_acc += sum(mindist) (fp64 accumulator, caller zeroes it). */
+SCD_API int scd_estep(const float* X, int64_t N, int D, const float* C, int K,
+              int64_t* labels, float* mindist /* nullable */, double* inertia_acc /* nullable */, scd_stream_t stream);
+
+/* Labelled-row inertia, faster_mix_k_means_pytorch.py:108-109: *acc += sum_i ||L[i]-C[labels[i]]||^2. */
+SCD_API int scd_labelled_inertia(const float* L, const int64_t* labels, int64_t n, int D, const float* C, int K,
+                         double* acc, scd_stream_t stream);
+
+/* M-step sums, faster_mix_k_means_pytorch.py:61-64 / :113-116 (native analogue: k_means_constrained/
+ * sklearn_import/cluster/_k_means.pyx:29-83): sums[k,:] = sum of rows with labels==k, counts[k] = #rows.
+ * Labels outside [0,K) are ignored.  sums/counts are overwritten.  Also leaves the label-sorted row order
+ * in the workspace (used by scd_vote).  Split from the divide so an all-reduce can sit between. */
+SCD_API size_t scd_mstep_workspace_bytes(int64_t N, int K);
+SCD_API int scd_mstep_sums(const float* X, const int64_t* labels, int64_t N, int D, int K,
+                   float* sums /* [K,D] */, int32_t* counts /* [K] */, void* ws, size_t ws_bytes, scd_stream_t stream);
+
+/* centers = sums / counts (empty cluster -> NaN row, like torch.mean over zero rows; no relocation), and
+ * faster_mix_k_means_pytorch.py:71 / :123: *shift = sum_k ||C_new[k]-C_old[k]||_2 (C_old, shift nullable).
+ * counts_f (nullable) takes float counts instead (e.g. after a packed fp32 all-reduce). ws: K floats. */
+SCD_API int scd_finalize_centers(const float* sums, const int32_t* counts, const float* counts_f, const float* C_old,
+                         float* C_new, float* shift, int K, int D, void* ws, size_t ws_bytes, scd_stream_t stream);
+
+/* ---------------------------------------------------------------- naming (a8, a9, a11) */
+
+/* zeroshot_weights [D,V] (V contiguous, clip_lang_util.py:107; row stride ldw elements; fp32 or bf16)
+ * -> Wt [V,D] bf16, the K-major operand layout.  One-off per vocabulary. */
+SCD_API int scd_vocab_prepare(const void* W, int w_is_bf16, int D, int64_t V, int64_t ldw, scd_bf16_t* Wt, scd_stream_t stream);
+SCD_API int scd_cast_bf16(const float* in, int64_t n, scd_bf16_t* out, scd_stream_t stream);
+/* out[r,:] = Wt[sel[r],:] - the K voted columns, main_unsup.py:601-602 / main_ptsup.py:668-669. */
+SCD_API int scd_gather_rows_bf16(const scd_bf16_t* Wt, const int64_t* sel, int n_sel, int D, int64_t V, scd_bf16_t* out,
+                         scd_stream_t stream);
+
+/* main_unsup.py:519-529, main_ptsup.py:538-543 (and :92-96, :116-120; k=1: main_unsup.py:610-614):
+ *   logits = scale * X @ Wt^T ; [softmax over V] ; top-k per row, largest first, ties -> lower index.
+ * X [N,D] bf16, Wt [V,D] bf16 (D <= 768, D % 8 == 0), k <= 8.  vals [N,k] fp32 (scaled logits, or softmax
+ * probabilities when want_softmax), idx [N,k] int64 = column + idx_offset (vocabulary-shard offset).
+ * row_max/row_sumexp (nullable, [N]): unscaled row max and sum exp(scale*(x-max)) for cross-shard softmax.
+ * The N x V score matrix is never written. */
+SCD_API size_t scd_name_topk_workspace_bytes(int64_t N, int64_t V, int k);
+SCD_API int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, int64_t V, float scale, int k,
+                  int want_softmax, int64_t idx_offset, float* vals, int64_t* idx,
+                  float* row_max, float* row_sumexp, void* ws, size_t ws_bytes, scd_stream_t stream);
+
+/* k-way merge of `parts` per-row top-k lists (vocabulary shards after an all-gather): [parts,N,k] -> [N,k].
+ * part_vals are scaled logits (as written by scd_name_topk without softmax); with want_softmax the
+ * per-part (row_max, row_sumexp) finish the softmax: p = exp(v - scale*M) / sum_p s_p*exp(scale*(m_p-M)). */
+SCD_API int scd_topk_merge(const float* part_vals, const int64_t* part_idx, const float* part_max, const float* part_sum,
+                   int parts, int64_t N, int k, float scale, int want_softmax, float* vals, int64_t* idx,
+                   scd_stream_t stream);
+
+/* main_unsup.py:575-582 / main_ptsup.py:636-644: per cluster c, Counter over topk_idx[cluster_of_row==c, :k_used]
+ * minus `excluded` names, then most_common(M) with Python's tie order (first occurrence in the row-major
+ * flattening).  out_names [K,M] int64 (-1 padded), out_counts [K,M], out_distinct [K] (#distinct names),
+ * out_rows [K] (#rows in cluster).  *overflow (device int) set to 1 if a cluster had more distinct names
+ * than the 16384-slot table. */
+SCD_API size_t scd_vote_workspace_bytes(int64_t N, int K);
+SCD_API int scd_vote(const int64_t* topk_idx, int k_total, int k_used, const int64_t* cluster_of_row, int64_t N, int K,
+             const int64_t* excluded, int n_excluded, int M, int64_t* out_names, int32_t* out_counts,
+             int32_t* out_distinct, int32_t* out_rows, int32_t* overflow, void* ws, size_t ws_bytes,
+             scd_stream_t stream);
+
+/* ---------------------------------------------------------------- host-side combinatorial step (a10) */
+
+/* gcd/project_utils/cluster_utils.py:234-275 linear_assignment (called from local_utils/clip_lang_util.py:178):
+ * Kuhn-Munkres on a HOST int64 cost matrix [n_rows,n_cols] with that implementation's tie-breaking.
+ * out_pairs: HOST buffer of 2*min(n_rows,n_cols) int64, (row,col) pairs sorted by (row,col). */
+SCD_API int scd_linear_assignment(const int64_t* cost, int n_rows, int n_cols, int64_t* out_pairs, int* n_pairs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCD_B200_H_ */

@@ -1,0 +1,64 @@
+"""ctypes binding of ``libscd_b200.so`` (the C ABI in ``include/scd_b200.h``).
+
+There is no fallback of any kind: if the library is missing, cannot be loaded, or a call fails, a
+``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'libscd_b200.so')
+
+_i64, _int, _f32, _sz, _vp = C.c_int64, C.c_int, C.c_float, C.c_size_t, C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/scd_b200.h declares
+SIGNATURES = {
+    'scd_version': (_int, []),
+    'scd_last_error': (C.c_char_p, []),
+    'scd_pairwise_distance': (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp]),
+    'scd_estep': (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _vp]),
+    'scd_labelled_inertia': (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp, _vp]),
+    'scd_mstep_workspace_bytes': (_sz, [_i64, _int]),
+    'scd_mstep_sums': (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _sz, _vp]),
+    'scd_finalize_centers': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _vp]),
+    'scd_vocab_prepare': (_int, [_vp, _int, _int, _i64, _i64, _vp, _vp]),
+    'scd_cast_bf16': (_int, [_vp, _i64, _vp, _vp]),
+    'scd_gather_rows_bf16': (_int, [_vp, _vp, _int, _int, _i64, _vp, _vp]),
+    'scd_name_topk_workspace_bytes': (_sz, [_i64, _i64, _int]),
+    'scd_name_topk': (_int, [_vp, _i64, _int, _vp, _i64, _f32, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'scd_topk_merge': (_int, [_vp, _vp, _vp, _vp, _int, _i64, _int, _f32, _int, _vp, _vp, _vp]),
+    'scd_vote_workspace_bytes': (_sz, [_i64, _int]),
+    'scd_vote': (_int, [_vp, _int, _int, _vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'scd_linear_assignment': (_int, [_vp, _int, _int, _vp, C.POINTER(_int)]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f'{LIB_PATH} is missing - build it with `python -m scd_b200.build` '
+                           '(scd_b200 has no CPU or library fallback)')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().scd_last_error()
+        raise RuntimeError(f'{what} failed: {msg.decode() if msg else "unknown error"}')
+
+
+def ptr(t) -> int | None:
+    """Device (or host) address of a torch tensor, None for None."""
+    return None if t is None else t.data_ptr()

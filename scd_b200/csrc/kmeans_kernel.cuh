@@ -1,0 +1,339 @@
+// k-means E-step / M-step kernels, fp32.
+//
+//   a1  pairwise_distance  local_utils/faster_mix_k_means_pytorch.py:177-212   dis[n,k] = sum_d (x-c)^2  (direct form)
+//   a2  E-step             :58-60 / :105-111    row min + argmin (ties -> lowest index, NaN wins) + inertia
+//   a3  M-step             :61-64 / :113-116    centers[j] = mean(X[labels == j]);  empty cluster -> NaN row
+//   a4  convergence        :71 / :123           shift = sum_k || c_k - c_k_old ||_2
+//
+// Layout in HBM: X [N, D] fp32 row-major, centroids [K, D] fp32 row-major, labels [N] int64 (the
+// reference's dtype), per-cluster sums [K, D] fp32 + counts [K] int32 (split from the divide so an
+// NCCL all-reduce can sit between when rows are sharded across GPUs).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace scd {
+
+// --------------------------------------------------------------------------------------------
+// Direct-form squared distance tile kernel.  Block = 256 threads, 128 rows x 64 centroids per
+// tile step, 16-wide d-chunks staged through shared memory (transposed, so the inner loop reads
+// float4 along rows / centroids), 8 x 4 accumulators per thread.
+//   FUSED = false : write the full [N, K] matrix (the pairwise_distance() drop-in; optional
+//                   int32 cost matrix round(1000 * sqrt(d)) for the size-constrained variant,
+//                   local_utils/sskm_constrained.py:116 + :324)
+//   FUSED = true  : keep a running (min, argmin) per row over all centroid tiles, write labels /
+//                   mindist and add the block's inertia (fp64) - the [N, K] matrix never exists.
+// --------------------------------------------------------------------------------------------
+constexpr int kDistBM = 128, kDistBN = 64, kDistBK = 16, kDistThreads = 256;
+
+__device__ __forceinline__ bool dist_better(float cand, float cur) {
+  // torch.min semantics: strict '<' keeps the lowest index among ties; a NaN beats any number.
+  return (cand < cur) || (cand != cand && cur == cur);
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kDistThreads)
+sqdist_kernel(const float* __restrict__ X, long long N, int D, const float* __restrict__ C, int K,
+              float* __restrict__ out, int* __restrict__ cost_x1000,
+              long long* __restrict__ labels, float* __restrict__ mindist, double* __restrict__ inertia) {
+  __shared__ __align__(16) float Xs[kDistBK][kDistBM + 4];
+  __shared__ __align__(16) float Cs[kDistBK][kDistBN + 4];
+  __shared__ float red_val[kDistBM][17];
+  __shared__ int red_idx[kDistBM][17];
+
+  const int tid = threadIdx.x;
+  const int tr = tid >> 4;          // 0..15 -> rows tr*8 .. tr*8+7
+  const int tc = tid & 15;          // 0..15 -> cols tc*4 .. tc*4+3
+  const long long row0 = (long long)blockIdx.x * kDistBM;
+
+  float best[8];
+  int best_k[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { best[i] = INFINITY; best_k[i] = 0; }
+  bool have[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) have[i] = false;
+
+  const int kt_begin = FUSED ? 0 : blockIdx.y;
+  const int kt_end = FUSED ? (K + kDistBN - 1) / kDistBN : blockIdx.y + 1;
+
+  for (int kt = kt_begin; kt < kt_end; ++kt) {
+    const int col0 = kt * kDistBN;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int d0 = 0; d0 < D; d0 += kDistBK) {
+      // stage X tile: 128 rows x 16 d  (2048 floats, 8 per thread), coalesced along d
+      {
+        const int r = tid >> 1;              // 0..127
+        const int dd = (tid & 1) * 8;        // 0 or 8
+        const long long gr = row0 + r;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int d = d0 + dd + q;
+          Xs[dd + q][r] = (gr < N && d < D) ? X[gr * D + d] : 0.f;
+        }
+      }
+      // stage C tile: 64 centroids x 16 d (1024 floats, 4 per thread)
+      {
+        const int c = tid >> 2;              // 0..63
+        const int dd = (tid & 3) * 4;
+        const int gc = col0 + c;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int d = d0 + dd + q;
+          Cs[dd + q][c] = (gc < K && d < D) ? C[(long long)gc * D + d] : 0.f;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < kDistBK; ++kk) {
+        const float4 xa = *reinterpret_cast<const float4*>(&Xs[kk][tr * 8]);
+        const float4 xb = *reinterpret_cast<const float4*>(&Xs[kk][tr * 8 + 4]);
+        const float4 cv = *reinterpret_cast<const float4*>(&Cs[kk][tc * 4]);
+        const float xr[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        const float cr[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float diff = xr[i] - cr[j];
+            acc[i][j] = fmaf(diff, diff, acc[i][j]);
+          }
+      }
+      __syncthreads();
+    }
+
+    if constexpr (!FUSED) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long gr = row0 + tr * 8 + i;
+        if (gr >= N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int gc = col0 + tc * 4 + j;
+          if (gc < K) {
+            if (out) out[gr * K + gc] = acc[i][j];
+            if (cost_x1000) cost_x1000[gr * K + gc] = (int)rintf(sqrtf(acc[i][j]) * 1000.f);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int gc = col0 + tc * 4 + j;
+          if (gc < K && (!have[i] || dist_better(acc[i][j], best[i]))) { best[i] = acc[i][j]; best_k[i] = gc; have[i] = true; }
+        }
+    }
+  }
+
+  if constexpr (FUSED) {
+    // reduce the 16 column-group candidates of each row (ascending centroid index inside a thread
+    // and across tc, so scanning tc upward with the same predicate keeps torch.min's tie rule)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { red_val[tr * 8 + i][tc] = best[i]; red_idx[tr * 8 + i][tc] = have[i] ? best_k[i] : -1; }
+    __syncthreads();
+    double local = 0.0;
+    if (tid < kDistBM) {
+      const long long gr = row0 + tid;
+      float bv = 0.f; int bk = -1;
+      for (int c = 0; c < 16; ++c) {
+        const int k = red_idx[tid][c];
+        if (k < 0) continue;
+        const float v = red_val[tid][c];
+        // candidates are not globally index-ordered across tc (each thread saw every tile), so
+        // compare on (value, index) explicitly
+        if (bk < 0 || dist_better(v, bv) || (v == bv && k < bk) || (v != v && bv != bv && k < bk)) { bv = v; bk = k; }
+      }
+      if (gr < N) {
+        labels[gr] = bk;
+        if (mindist) mindist[gr] = bv;
+        local = (double)bv;
+      }
+    }
+    // block inertia: warp shuffle then one fp64 atomic per warp
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_down_sync(0xffffffffu, local, off);
+    if ((tid & 31) == 0 && tid < kDistBM && inertia) atomicAdd(inertia, local);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// M-step, part 1: counting sort of row ids by label (histogram -> exclusive scan -> scatter).
+// Labels outside [0, K) (e.g. the reference's -1 "unassigned") are ignored.
+// --------------------------------------------------------------------------------------------
+__global__ void label_hist_kernel(const long long* __restrict__ labels, long long N, int K, int* __restrict__ counts) {
+  extern __shared__ int sh_hist[];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) sh_hist[k] = 0;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    const long long l = labels[i];
+    if (l >= 0 && l < K) atomicAdd(&sh_hist[(int)l], 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) if (sh_hist[k]) atomicAdd(&counts[k], sh_hist[k]);
+}
+
+// single block: offsets[k] = sum_{j<k} counts[j]; offsets[K] = total; cursor[k] = offsets[k]
+__global__ void label_scan_kernel(const int* __restrict__ counts, int K, int* __restrict__ offsets, int* __restrict__ cursor) {
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < K; base += 1024) {
+    const int k = base + threadIdx.x;
+    const int v = k < K ? counts[k] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      const int t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    const int excl = carry + sh[threadIdx.x] - v;
+    if (k < K) { offsets[k] = excl; cursor[k] = excl; }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[K] = carry;
+}
+
+__global__ void label_scatter_kernel(const long long* __restrict__ labels, long long N, int K, int* __restrict__ cursor,
+                                     int* __restrict__ order) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    const long long l = labels[i];
+    if (l >= 0 && l < K) order[atomicAdd(&cursor[(int)l], 1)] = (int)i;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// M-step, part 2: segmented sum over the label-sorted row order.  One warp owns kSegRows
+// consecutive sorted positions; lane l keeps D/128 float4 accumulators (columns j*128 + 4l..4l+3,
+// so every row read is one coalesced 512 B request per j); when the cluster id changes, or at the
+// end of the chunk, the warp flushes with vector reductions (red.global.add.v4.f32) into sums[k].
+// Atomics per (cluster, column) ~ rows_in_cluster / kSegRows instead of rows_in_cluster.
+// --------------------------------------------------------------------------------------------
+constexpr int kSegRows = 64;
+constexpr int kSegMaxVec = 8;      // supports D <= 1024 (D % 4 == 0)
+
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+segment_sum_kernel(const float* __restrict__ X, const int* __restrict__ order, const int* __restrict__ offsets,
+                   int K, int D, float* __restrict__ sums) {
+  const int total = offsets[K];
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int p0 = warp_global * kSegRows;
+  if (p0 >= total) return;
+  const int p1 = min(p0 + kSegRows, total);
+  const int nvec = D >> 7;                       // float4 per lane for the 128-column-aligned part
+  const int tail = D - (nvec << 7);              // < 128 remaining columns (multiple of 4)
+  // cluster of the first position: binary search in offsets
+  int lo = 0, hi = K;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offsets[mid] <= p0) lo = mid; else hi = mid; }
+  int k = lo;
+  while (k < K - 1 && offsets[k + 1] <= p0) ++k;   // skip empty clusters
+  float4 acc[kSegMaxVec];
+#pragma unroll
+  for (int j = 0; j < kSegMaxVec; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc_tail = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool tail_lane = (lane * 4) < tail;
+
+  auto flush = [&](int kk) {
+    float* dst = sums + (long long)kk * D;
+#pragma unroll
+    for (int j = 0; j < kSegMaxVec; ++j)
+      if (j < nvec) { red_add_v4(dst + j * 128 + lane * 4, acc[j]); acc[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    if (tail_lane) { red_add_v4(dst + nvec * 128 + lane * 4, acc_tail); acc_tail = make_float4(0.f, 0.f, 0.f, 0.f); }
+  };
+
+  int seg_end = offsets[k + 1];
+  for (int p = p0; p < p1; ++p) {
+    while (p >= seg_end) { flush(k); ++k; seg_end = offsets[k + 1]; }
+    const float* src = X + (long long)order[p] * D;
+#pragma unroll
+    for (int j = 0; j < kSegMaxVec; ++j)
+      if (j < nvec) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + j * 128 + lane * 4));
+        acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
+      }
+    if (tail_lane) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + nvec * 128 + lane * 4));
+      acc_tail.x += v.x; acc_tail.y += v.y; acc_tail.z += v.z; acc_tail.w += v.w;
+    }
+  }
+  flush(k);
+}
+
+// centers = sums / counts (0/0 -> NaN, as torch's mean over zero rows), per-cluster move norm
+__global__ void finalize_centers_kernel(const float* __restrict__ sums, const float* __restrict__ counts_f, const int* __restrict__ counts_i,
+                                        const float* __restrict__ c_old, float* __restrict__ c_new, float* __restrict__ move_norm,
+                                        int K, int D) {
+  const int k = blockIdx.x;
+  const float cnt = counts_i ? (float)counts_i[k] : counts_f[k];
+  float part = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float c = sums[(long long)k * D + d] / cnt;
+    c_new[(long long)k * D + d] = c;
+    if (c_old) { const float df = c - c_old[(long long)k * D + d]; part += df * df; }
+  }
+  __shared__ float sh[32];
+  for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += sh[w];
+    if (move_norm) move_norm[k] = sqrtf(t);
+  }
+}
+
+// shift = sum_k move_norm[k], one block, fixed order (deterministic)
+__global__ void sum_small_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  __shared__ float sh[1024];
+  float t = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) t += v[i];
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+    if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
+// a4 labelled inertia, ref :108-109: sum_i || L_i - C[label_i] ||^2  (one warp per row, fp64 atomic per block)
+__global__ void __launch_bounds__(256)
+gather_sqdist_kernel(const float* __restrict__ L, const long long* __restrict__ labels, long long n, int D,
+                     const float* __restrict__ C, int K, double* __restrict__ acc) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  float part = 0.f;
+  if (row < n) {
+    const long long l = labels[row];
+    if (l >= 0 && l < K) {
+      for (int d = lane; d < D; d += 32) { const float df = L[row * D + d] - C[l * D + d]; part = fmaf(df, df, part); }
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+  __shared__ double sh[8];
+  if (lane == 0) sh[threadIdx.x >> 5] = (double)part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    atomicAdd(acc, t);
+  }
+}
+
+}  // namespace scd

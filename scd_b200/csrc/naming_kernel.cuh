@@ -1,0 +1,345 @@
+// Image x vocabulary scoring with a fused per-row top-k epilogue.
+//
+//   scores[n, v] = sum_d X[n, d] * Wt[v, d]          X: [N, 768] bf16 row-major (K-major A)
+//                                                    Wt: [V, 768] bf16 row-major (K-major B), the
+//                                                    one-off transpose of the reference's [D, V]
+//   replaces  main_unsup.py:519-529 / main_ptsup.py:538-543 (GEMM -> [1024, V] logits in HBM ->
+//   softmax -> topk twice) and main_unsup.py:610-614 (k = 1 over the K selected columns).
+//
+// The N x V score matrix never exists: a CTA pair (cta_group::2, 256 x 256 x 16 tcgen05.mma) keeps its
+// 256 image rows stationary in shared memory (2 x 12 k-blocks x 16 KB, SWIZZLE_128B), streams the
+// vocabulary through a 4-stage TMA ring (SWIZZLE_64B, 32 k per stage), accumulates each
+// 256 x 256 tile in TMEM (2 x 256 columns, double buffered) and the four epilogue warps read the
+// tile back with tcgen05.ld - one thread per image row - keeping a sorted running top-k (and, for
+// the unsupervised driver's softmax, a running max / sum-exp) in registers.  Only [N, k] leaves.
+//
+// Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer (leader CTA only), 2 = TMEM
+// allocator, 3 = idle, 4..7 = epilogue (TMEM lane quadrant = warp & 3).
+#pragma once
+#include "ptx.cuh"
+#include <cuda_bf16.h>
+
+namespace scd {
+
+constexpr int kNameMaxD = 768;         // widest embedding the stationary A buffer holds (any D <= 768, D % 8 == 0)
+constexpr int kBlockM = 128;           // rows per CTA (256 per pair)
+constexpr int kTileN = 256;            // vocabulary entries per accumulator tile (128 loaded per CTA)
+constexpr int kAKBlock = 64;           // k per stationary A block  (128 B rows, SWIZZLE_128B)
+constexpr int kNumAKBlocks = kNameMaxD / kAKBlock;   // 12 (capacity; the live count is NameParams::num_kb)
+constexpr int kBK = 32;                // k per B stage            (64 B rows, SWIZZLE_64B)
+constexpr int kBStages = 4;
+constexpr int kABlockBytes = kBlockM * kAKBlock * 2;     // 16384
+constexpr int kBStageBytes = (kTileN / 2) * kBK * 2;     // 8192 per CTA
+constexpr int kNameThreads = 256;
+constexpr int kTmemCols = 512;
+
+struct NameSmem {
+  // offsets inside dynamic shared memory (base aligned to 1024)
+  static constexpr int a_off = 0;
+  static constexpr int b_off = kNumAKBlocks * kABlockBytes;                 // 196608
+  static constexpr int bar_off = b_off + kBStages * kBStageBytes;           // 229376
+  // barriers (8 B each)
+  static constexpr int full_bar = bar_off;                                  // [kBStages]
+  static constexpr int empty_bar = full_bar + 8 * kBStages;                 // [kBStages]
+  static constexpr int a_full_bar = empty_bar + 8 * kBStages;               // [12]
+  static constexpr int a_empty_bar = a_full_bar + 8 * kNumAKBlocks;         // [12]
+  static constexpr int tmem_full_bar = a_empty_bar + 8 * kNumAKBlocks;      // [2]
+  static constexpr int tmem_empty_bar = tmem_full_bar + 16;                 // [2]
+  static constexpr int tmem_ptr = tmem_empty_bar + 16;
+  static constexpr int total = tmem_ptr + 16;
+};
+static_assert(NameSmem::total <= 232448, "exceeds 227 KB of shared memory");
+
+struct NameParams {
+  long long n_rows;        // N
+  long long v_total;       // V (this rank's vocabulary slice length)
+  int n_vsplit;            // vocabulary chunks per row block (work items = row blocks x chunks)
+  int tiles_per_chunk;     // 256-wide tiles per chunk
+  int n_row_blocks;        // ceil(N / 256)
+  int num_kb;              // ceil(D / 64) live A k-blocks (TMA zero-fills the ragged end of D)
+  int want_softmax;
+  float scale_log2e;       // scale * log2(e) for the running sum-exp
+  // partial results, one slot per vocabulary chunk: [n_vsplit][N][KT] / [n_vsplit][N]
+  float* part_val;
+  int* part_idx;
+  float* part_max;
+  float* part_sum;
+};
+
+// One sorted running top-KT list in registers.  Strict '>' everywhere: among equal scores the
+// lower vocabulary index stays in front (columns are visited in increasing order).
+template <int KT>
+struct TopK {
+  float v[KT];
+  int i[KT];
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int j = 0; j < KT; ++j) { v[j] = -INFINITY; i[j] = -1; }
+  }
+  __device__ __forceinline__ float floor_val() const { return v[KT - 1]; }
+  __device__ __forceinline__ void push(float x, int col) {
+    if (x > v[KT - 1]) {
+      v[KT - 1] = x; i[KT - 1] = col;
+#pragma unroll
+      for (int j = KT - 1; j > 0; --j) {
+        if (v[j] > v[j - 1]) {
+          float tv = v[j]; v[j] = v[j - 1]; v[j - 1] = tv;
+          int ti = i[j]; i[j] = i[j - 1]; i[j - 1] = ti;
+        }
+      }
+    }
+  }
+};
+
+template <int KT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNameThreads, 1)
+name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                 const NameParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need a 1024-aligned base; both CTAs of the pair compute the same offset
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = ptx::smem_u32(smem);
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
+  const int n_items = p.n_row_blocks * p.n_vsplit;
+  const int tiles_total = (int)((p.v_total + kTileN - 1) / kTileN);
+
+  const int nkb = p.num_kb;
+  auto full_bar = [&](int s) { return sbase + NameSmem::full_bar + 8 * s; };
+  auto empty_bar = [&](int s) { return sbase + NameSmem::empty_bar + 8 * s; };
+  auto a_full_bar = [&](int kb) { return sbase + NameSmem::a_full_bar + 8 * kb; };
+  auto a_empty_bar = [&](int kb) { return sbase + NameSmem::a_empty_bar + 8 * kb; };
+  auto tmem_full_bar = [&](int b) { return sbase + NameSmem::tmem_full_bar + 8 * b; };
+  auto tmem_empty_bar = [&](int b) { return sbase + NameSmem::tmem_empty_bar + 8 * b; };
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_x);
+    ptx::prefetch_tensormap(&map_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kBStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int kb = 0; kb < kNumAKBlocks; ++kb) { ptx::mbar_init(a_full_bar(kb), 1); ptx::mbar_init(a_empty_bar(kb), 1); }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(tmem_full_bar(b), 1);
+      ptx::mbar_init(tmem_empty_bar(b), 8);      // 4 epilogue warps x 2 CTAs arrive on the leader's copy
+    }
+    ptx::fence_mbar_init_cluster();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<2>(sbase + NameSmem::tmem_ptr, kTmemCols);
+    ptx::tmem_relinquish<2>();
+  }
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + NameSmem::tmem_ptr);
+
+  // work item -> (row block, first tile, tile count)
+  auto item_rb = [&](int it) { return it / p.n_vsplit; };
+  auto item_tile0 = [&](int it) { return (it % p.n_vsplit) * p.tiles_per_chunk; };
+  auto item_ntiles = [&](int it) {
+    int t0 = item_tile0(it);
+    int t1 = min(t0 + p.tiles_per_chunk, tiles_total);
+    return max(t1 - t0, 0);
+  };
+
+  if (warp == 0) {
+    // ======================================================= TMA producer (one lane)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int my_item_no = 0;                       // how many items this pair has started (A buffer reuse count)
+      auto load_a = [&](int it, int reuse, int kb) {
+        ptx::mbar_wait(a_empty_bar(kb), (reuse & 1) ^ 1, 100 + kb);
+        if (leader) ptx::mbar_arrive_expect_tx(a_full_bar(kb), 2 * kABlockBytes);
+        const int row0 = item_rb(it) * 2 * kBlockM + (int)cta_rank * kBlockM;
+        ptx::tma_load_2d<2>(sbase + NameSmem::a_off + kb * kABlockBytes, &map_x,
+                            a_full_bar(kb) & ptx::kPeerBitMask, kb * kAKBlock, row0, ptx::kEvictFirst);
+      };
+      for (int it = pair; it < n_items; it += n_pairs, ++my_item_no) {
+        if (my_item_no == 0) {
+          for (int kb = 0; kb < nkb; ++kb) load_a(it, 0, kb);
+        }
+        const int nt = item_ntiles(it);
+        const int next_it = it + n_pairs;
+        const bool has_next = next_it < n_items;
+        for (int t = 0; t < nt; ++t) {
+          const int v0 = (item_tile0(it) + t) * kTileN + (int)cta_rank * (kTileN / 2);
+          const bool last_tile = (t == nt - 1);
+          for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+            for (int h = 0; h < kAKBlock / kBK; ++h) {
+              ptx::mbar_wait(empty_bar(stage), phase ^ 1, 200 + stage);
+              if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * kBStageBytes);
+              ptx::tma_load_2d<2>(sbase + NameSmem::b_off + stage * kBStageBytes, &map_w,
+                                  full_bar(stage) & ptx::kPeerBitMask, kb * kAKBlock + h * kBK, v0, ptx::kEvictLast);
+              if (++stage == kBStages) { stage = 0; phase ^= 1; }
+            }
+            // the A block two steps back was released by the MMAs we just queued behind: refill it
+            // with the next item's rows while this item's last tile is still running
+            if (last_tile && has_next && kb >= 2) load_a(next_it, my_item_no + 1, kb - 2);
+          }
+        }
+        if (has_next) {
+          const int first_left = nt == 0 ? 0 : max(nkb - 2, 0);
+          for (int kb = first_left; kb < nkb; ++kb) load_a(next_it, my_item_no + 1, kb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================= MMA issuer (leader CTA, one lane)
+    if (leader && lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16_f32(2 * kBlockM, kTileN);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t tile_no = 0;
+      int my_item_no = 0;
+      for (int it = pair; it < n_items; it += n_pairs, ++my_item_no) {
+        const int nt = item_ntiles(it);
+        for (int t = 0; t < nt; ++t, ++tile_no) {
+          const uint32_t buf = tile_no & 1u;
+          ptx::mbar_wait(tmem_empty_bar(buf), ((tile_no >> 1) & 1u) ^ 1u, 300 + buf);
+          ptx::tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + buf * kTileN;
+          for (int kb = 0; kb < nkb; ++kb) {
+            if (t == 0) { ptx::mbar_wait(a_full_bar(kb), my_item_no & 1, 400 + kb); ptx::tc_fence_after_sync(); }
+            const uint32_t a_addr = sbase + NameSmem::a_off + kb * kABlockBytes;
+#pragma unroll
+            for (int h = 0; h < kAKBlock / kBK; ++h) {
+              ptx::mbar_wait(full_bar(stage), phase, 500 + stage);
+              ptx::tc_fence_after_sync();
+              const uint32_t b_addr = sbase + NameSmem::b_off + stage * kBStageBytes;
+#pragma unroll
+              for (int kk = 0; kk < kBK / 16; ++kk) {
+                const uint64_t adesc = ptx::make_kmajor_desc(a_addr + (h * kBK + kk * 16) * 2, 128);
+                const uint64_t bdesc = ptx::make_kmajor_desc(b_addr + kk * 16 * 2, 64);
+                ptx::umma_bf16<2>(d_tmem, adesc, bdesc, idesc, (kb | h | kk) != 0 ? 1u : 0u);
+              }
+              ptx::umma_commit<2>(empty_bar(stage), 0b11);
+              if (++stage == kBStages) { stage = 0; phase ^= 1; }
+            }
+            if (t == nt - 1) ptx::umma_commit<2>(a_empty_bar(kb), 0b11);
+          }
+          ptx::umma_commit<2>(tmem_full_bar(buf), 0b11);
+        }
+        if (nt == 0) { for (int kb = 0; kb < nkb; ++kb) { ptx::mbar_wait(a_full_bar(kb), my_item_no & 1, 450 + kb); ptx::umma_commit<2>(a_empty_bar(kb), 0b11); } }
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================================= epilogue: one thread per image row
+    const uint32_t quad = warp & 3u;
+    const uint32_t lane_addr = (quad * 32u) << 16;
+    uint32_t tile_no = 0;
+    TopK<KT> top;
+    for (int it = pair; it < n_items; it += n_pairs) {
+      const int nt = item_ntiles(it);
+      const long long row = (long long)item_rb(it) * 2 * kBlockM + cta_rank * kBlockM + quad * 32 + lane;
+      top.reset();
+      float run_max = -INFINITY, run_sum = 0.f;
+      for (int t = 0; t < nt; ++t, ++tile_no) {
+        const uint32_t buf = tile_no & 1u;
+        const int col0 = (item_tile0(it) + t) * kTileN;
+        const int n_valid = (int)min((long long)kTileN, p.v_total - col0);
+        ptx::mbar_wait(tmem_full_bar(buf), (tile_no >> 1) & 1u, 600 + buf);
+        ptx::tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + lane_addr + buf * kTileN;
+#pragma unroll 1
+        for (int c = 0; c < kTileN / 32; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, r);
+          ptx::tmem_ld_wait();
+          const int cbase = c * 32;
+          if (cbase >= n_valid) continue;
+          if (cbase + 32 > n_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (cbase + j >= n_valid) r[j] = 0xff800000u;   // -inf
+          }
+          float cmax = __uint_as_float(r[0]);
+#pragma unroll
+          for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(r[j]));
+          if (p.want_softmax) {
+            if (cmax > run_max) { run_sum *= exp2f((run_max - cmax) * p.scale_log2e); run_max = cmax; }
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc += exp2f((__uint_as_float(r[j]) - run_max) * p.scale_log2e);
+            run_sum += acc;
+          }
+          if (cmax > top.floor_val()) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) top.push(__uint_as_float(r[j]), col0 + cbase + j);
+          }
+        }
+        // accumulator buffer drained: hand it back to the MMA issuer (leader's barrier)
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(tmem_empty_bar(buf) & ptx::kPeerBitMask);
+      }
+      if (row < p.n_rows) {
+        const long long slot = (long long)(it % p.n_vsplit) * p.n_rows + row;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) { p.part_val[slot * KT + j] = top.v[j]; p.part_idx[slot * KT + j] = top.i[j]; }
+        p.part_max[slot] = run_max;
+        p.part_sum[slot] = run_sum;
+      }
+    }
+  }
+
+  // teardown: nobody may free TMEM / exit while the peer can still touch this CTA's memory
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync_all();
+  if (warp == 2) ptx::tmem_dealloc<2>(tmem_base, kTmemCols);
+}
+
+// Merge `parts` partial top-k lists per row (vocabulary chunks of one GPU: IdxT=int, raw accumulators;
+// or the all-gathered lists of several vocabulary shards: IdxT=long long, PRESCALED values) into the
+// final sorted top-k: value descending, ties -> lower index.  Also finishes the optional softmax:
+//   p_j = exp(scale * (v_j - M)) / sum_parts s_p * exp(scale * (m_p - M)).
+template <typename IdxT, bool PRESCALED>
+__global__ void topk_merge_kernel(const float* __restrict__ part_val, const IdxT* __restrict__ part_idx,
+                                  const float* __restrict__ part_max, const float* __restrict__ part_sum,
+                                  int parts, long long n_rows, int kt_in, int k_out, float scale, int want_softmax,
+                                  long long idx_offset, float* __restrict__ out_val, long long* __restrict__ out_idx,
+                                  float* __restrict__ out_max, float* __restrict__ out_sum) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  float bv[8]; long long bi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { bv[j] = -INFINITY; bi[j] = -1; }
+  float M = -INFINITY;
+  for (int q = 0; q < parts; ++q) {
+    const long long slot = (long long)q * n_rows + row;
+    for (int j = 0; j < kt_in; ++j) {
+      const float x = part_val[slot * kt_in + j];
+      const long long id = (long long)part_idx[slot * kt_in + j];
+      if (id < 0) continue;
+      int pos = k_out;                       // insert keeping (value desc, index asc)
+      for (int s = k_out - 1; s >= 0; --s) {
+        if (bi[s] < 0 || x > bv[s] || (x == bv[s] && id < bi[s])) pos = s; else break;
+      }
+      if (pos < k_out) {
+        for (int s = k_out - 1; s > pos; --s) { bv[s] = bv[s - 1]; bi[s] = bi[s - 1]; }
+        bv[pos] = x; bi[pos] = id;
+      }
+    }
+    if (part_max) M = fmaxf(M, part_max[slot]);
+  }
+  float S = 0.f;
+  if (part_max) {
+    for (int q = 0; q < parts; ++q) {
+      const long long slot = (long long)q * n_rows + row;
+      const float m = part_max[slot];
+      if (m > -INFINITY) S += part_sum[slot] * expf(scale * (m - M));
+    }
+    if (out_max) { out_max[row] = M; out_sum[row] = S; }
+  }
+  for (int j = 0; j < k_out; ++j) {
+    float val = PRESCALED ? bv[j] : bv[j] * scale;
+    if (want_softmax) val = (PRESCALED ? expf(bv[j] - scale * M) : expf(scale * (bv[j] - M))) / S;
+    out_val[row * k_out + j] = val;
+    out_idx[row * k_out + j] = bi[j] < 0 ? -1 : bi[j] + idx_offset;
+  }
+}
+
+}  // namespace scd

@@ -1,0 +1,398 @@
+// C ABI of scd_b200 (see include/scd_b200.h): argument checking, workspace carving, tensor-map
+// construction and kernel launches.  No allocation, no synchronisation.
+#include "../../include/scd_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "kmeans_kernel.cuh"
+#include "naming_kernel.cuh"
+#include "vote_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return 1;
+}
+
+#define SCD_CUDA(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(_e));    \
+  } while (0)
+
+#define SCD_LAUNCH_CHECK(name)                                                             \
+  do {                                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess) return fail("launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+inline cudaStream_t as_stream(scd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int device_sm_count() {
+  static int cached = 0;
+  if (cached) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  cached = n;
+  return n;
+}
+
+// ---------------------------------------------------------------- tensor maps
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, box_cols], inner (cols) swizzled
+int make_map_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
+                  CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)", (int)r,
+                                     (unsigned long long)rows, (unsigned long long)cols);
+  return 0;
+}
+
+// ---------------------------------------------------------------- naming plan
+struct NamePlan {
+  int kt;                 // compiled list length (1, 5 or 8)
+  int n_row_blocks;
+  int tiles_total;
+  int n_vsplit;
+  int tiles_per_chunk;
+  int n_pairs;
+  size_t off_val, off_idx, off_max, off_sum, bytes;
+};
+
+bool plan_naming(int64_t N, int64_t V, int k, NamePlan* pl) {
+  if (k < 1 || k > 8) return false;
+  pl->kt = k == 1 ? 1 : (k <= 5 ? 5 : 8);
+  pl->n_row_blocks = (int)((N + 2 * scd::kBlockM - 1) / (2 * scd::kBlockM));
+  pl->tiles_total = (int)((V + scd::kTileN - 1) / scd::kTileN);
+  const int pairs_hw = std::max(1, device_sm_count() / 2);
+  // pick the vocabulary split that fills the CTA pairs best (items = row blocks x chunks)
+  int best_s = 1;
+  double best_eff = -1.0;
+  const int max_s = std::max(1, std::min(pl->tiles_total, 16));
+  for (int s = 1; s <= max_s; ++s) {
+    const int tpc = (pl->tiles_total + s - 1) / s;
+    const int s_eff = (pl->tiles_total + tpc - 1) / tpc;
+    if (s_eff != s) continue;
+    const long long items = (long long)pl->n_row_blocks * s;
+    const long long waves = (items + pairs_hw - 1) / pairs_hw;
+    // useful tile-steps over issued tile-steps, with a small charge per extra A reload
+    const double eff = (double)pl->n_row_blocks * pl->tiles_total / ((double)waves * pairs_hw * tpc) - 0.004 * (s - 1);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_s = s; }
+  }
+  pl->n_vsplit = std::max(1, best_s);
+  pl->tiles_per_chunk = std::max(1, (pl->tiles_total + pl->n_vsplit - 1) / pl->n_vsplit);
+  const long long items = (long long)pl->n_row_blocks * pl->n_vsplit;
+  pl->n_pairs = (int)std::max<long long>(1, std::min<long long>(pairs_hw, items));
+  size_t o = 0;
+  const size_t slots = (size_t)pl->n_vsplit * (size_t)N;
+  pl->off_val = o; o = align_up(o + slots * pl->kt * sizeof(float), 256);
+  pl->off_idx = o; o = align_up(o + slots * pl->kt * sizeof(int), 256);
+  pl->off_max = o; o = align_up(o + slots * sizeof(float), 256);
+  pl->off_sum = o; o = align_up(o + slots * sizeof(float), 256);
+  pl->bytes = std::max<size_t>(o, 256);
+  return true;
+}
+
+template <int KT>
+int launch_name_topk(const CUtensorMap& mx, const CUtensorMap& mw, const scd::NameParams& p, int n_pairs, cudaStream_t st) {
+  static bool attr_set = false;
+  const int smem = scd::NameSmem::total + 1024;
+  if (!attr_set) {
+    SCD_CUDA(cudaFuncSetAttribute(scd::name_topk_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  scd::name_topk_kernel<KT><<<2 * n_pairs, scd::kNameThreads, smem, st>>>(mx, mw, p);
+  SCD_LAUNCH_CHECK("name_topk_kernel");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int scd_version(void) { return 100; }
+
+const char* scd_last_error(void) { return g_last_error.c_str(); }
+
+// ============================================================================ k-means
+int scd_pairwise_distance(const float* X, int64_t N, int D, const float* C, int K, float* out, int32_t* cost_x1000,
+                          scd_stream_t stream) {
+  if (N < 0 || D <= 0 || K <= 0) return fail("scd_pairwise_distance: bad shape N=%lld D=%d K=%d", (long long)N, D, K);
+  if (N == 0) return 0;
+  if (!X || !C || (!out && !cost_x1000)) return fail("scd_pairwise_distance: null pointer");
+  dim3 grid((unsigned)((N + scd::kDistBM - 1) / scd::kDistBM), (unsigned)((K + scd::kDistBN - 1) / scd::kDistBN));
+  scd::sqdist_kernel<false><<<grid, scd::kDistThreads, 0, as_stream(stream)>>>(X, N, D, C, K, out, cost_x1000, nullptr, nullptr, nullptr);
+  SCD_LAUNCH_CHECK("sqdist_kernel<full>");
+  return 0;
+}
+
+int scd_estep(const float* X, int64_t N, int D, const float* C, int K, int64_t* labels, float* mindist, double* inertia_acc,
+              scd_stream_t stream) {
+  if (N < 0 || D <= 0 || K <= 0) return fail("scd_estep: bad shape N=%lld D=%d K=%d", (long long)N, D, K);
+  if (N == 0) return 0;
+  if (!X || !C || !labels) return fail("scd_estep: null pointer");
+  dim3 grid((unsigned)((N + scd::kDistBM - 1) / scd::kDistBM));
+  scd::sqdist_kernel<true><<<grid, scd::kDistThreads, 0, as_stream(stream)>>>(X, N, D, C, K, nullptr, nullptr,
+                                                                              reinterpret_cast<long long*>(labels), mindist, inertia_acc);
+  SCD_LAUNCH_CHECK("sqdist_kernel<fused argmin>");
+  return 0;
+}
+
+int scd_labelled_inertia(const float* L, const int64_t* labels, int64_t n, int D, const float* C, int K, double* acc,
+                         scd_stream_t stream) {
+  if (n < 0 || D <= 0 || K <= 0) return fail("scd_labelled_inertia: bad shape");
+  if (n == 0) return 0;
+  if (!L || !labels || !C || !acc) return fail("scd_labelled_inertia: null pointer");
+  const long long threads = n * 32;
+  scd::gather_sqdist_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(
+      L, reinterpret_cast<const long long*>(labels), n, D, C, K, acc);
+  SCD_LAUNCH_CHECK("gather_sqdist_kernel");
+  return 0;
+}
+
+// workspace layout (ints): offsets[K+1] | cursor[K] | order[N]
+size_t scd_mstep_workspace_bytes(int64_t N, int K) {
+  return align_up((size_t)(2 * (size_t)K + 1 + (size_t)std::max<int64_t>(N, 0)) * sizeof(int), 256) + 256;
+}
+
+static int sort_rows_by_label(const int64_t* labels, int64_t N, int K, int32_t* counts, int* offsets, int* cursor, int* order,
+                              cudaStream_t st) {
+  SCD_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)K, st));
+  const int blocks = (int)std::min<long long>((N + 255) / 256, 148 * 8);
+  if (N > 0) {
+    scd::label_hist_kernel<<<blocks, 256, sizeof(int) * (size_t)K, st>>>(reinterpret_cast<const long long*>(labels), N, K, counts);
+    SCD_LAUNCH_CHECK("label_hist_kernel");
+  }
+  scd::label_scan_kernel<<<1, 1024, 0, st>>>(counts, K, offsets, cursor);
+  SCD_LAUNCH_CHECK("label_scan_kernel");
+  if (N > 0) {
+    scd::label_scatter_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(labels), N, K, cursor, order);
+    SCD_LAUNCH_CHECK("label_scatter_kernel");
+  }
+  return 0;
+}
+
+int scd_mstep_sums(const float* X, const int64_t* labels, int64_t N, int D, int K, float* sums, int32_t* counts, void* ws,
+                   size_t ws_bytes, scd_stream_t stream) {
+  if (N < 0 || D <= 0 || K <= 0) return fail("scd_mstep_sums: bad shape N=%lld D=%d K=%d", (long long)N, D, K);
+  if (N >= (1ll << 31)) return fail("scd_mstep_sums: N=%lld exceeds the int32 row-index range", (long long)N);
+  if (D % 4 != 0 || D > 128 * scd::kSegMaxVec + 124) return fail("scd_mstep_sums: D=%d must be a multiple of 4 and <= %d", D, 128 * scd::kSegMaxVec + 124);
+  if (K * sizeof(int) > 48 * 1024) return fail("scd_mstep_sums: K=%d too large for the shared-memory histogram", K);
+  if (!sums || !counts || !ws) return fail("scd_mstep_sums: null pointer");
+  if (ws_bytes < scd_mstep_workspace_bytes(N, K)) return fail("scd_mstep_sums: workspace too small (%zu < %zu)", ws_bytes, scd_mstep_workspace_bytes(N, K));
+  if ((reinterpret_cast<uintptr_t>(X) & 15) != 0) return fail("scd_mstep_sums: X must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  int* offsets = reinterpret_cast<int*>(ws);
+  int* cursor = offsets + K + 1;
+  int* order = cursor + K;
+  SCD_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * (size_t)K * D, st));
+  if (int e = sort_rows_by_label(labels, N, K, counts, offsets, cursor, order, st)) return e;
+  if (N > 0) {
+    const long long warps = (N + scd::kSegRows - 1) / scd::kSegRows;
+    const long long blocks = (warps * 32 + 255) / 256;
+    scd::segment_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, order, offsets, K, D, sums);
+    SCD_LAUNCH_CHECK("segment_sum_kernel");
+  }
+  return 0;
+}
+
+int scd_finalize_centers(const float* sums, const int32_t* counts, const float* counts_f, const float* C_old, float* C_new,
+                         float* shift, int K, int D, void* ws, size_t ws_bytes, scd_stream_t stream) {
+  if (K <= 0 || D <= 0) return fail("scd_finalize_centers: bad shape");
+  if (!sums || (!counts && !counts_f) || !C_new) return fail("scd_finalize_centers: null pointer");
+  if (shift && (!C_old || !ws || ws_bytes < sizeof(float) * (size_t)K)) return fail("scd_finalize_centers: shift needs C_old and K floats of workspace");
+  cudaStream_t st = as_stream(stream);
+  float* norms = shift ? reinterpret_cast<float*>(ws) : nullptr;
+  scd::finalize_centers_kernel<<<K, 256, 0, st>>>(sums, counts_f, counts, C_old, C_new, norms, K, D);
+  SCD_LAUNCH_CHECK("finalize_centers_kernel");
+  if (shift) {
+    scd::sum_small_kernel<<<1, 1024, 0, st>>>(norms, K, shift);
+    SCD_LAUNCH_CHECK("sum_small_kernel");
+  }
+  return 0;
+}
+
+// ============================================================================ naming
+int scd_vocab_prepare(const void* W, int w_is_bf16, int D, int64_t V, int64_t ldw, scd_bf16_t* Wt, scd_stream_t stream) {
+  if (D <= 0 || V < 0 || ldw < V) return fail("scd_vocab_prepare: bad shape D=%d V=%lld ldw=%lld", D, (long long)V, (long long)ldw);
+  if (V == 0) return 0;
+  if (!W || !Wt) return fail("scd_vocab_prepare: null pointer");
+  dim3 grid((unsigned)((V + 31) / 32), (unsigned)((D + 31) / 32)), block(32, 8);
+  if (w_is_bf16)
+    scd::transpose_to_bf16_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(W), D, V, ldw,
+                                                                                         reinterpret_cast<__nv_bfloat16*>(Wt));
+  else
+    scd::transpose_to_bf16_kernel<float><<<grid, block, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(W), D, V, ldw,
+                                                                                 reinterpret_cast<__nv_bfloat16*>(Wt));
+  SCD_LAUNCH_CHECK("transpose_to_bf16_kernel");
+  return 0;
+}
+
+int scd_cast_bf16(const float* in, int64_t n, scd_bf16_t* out, scd_stream_t stream) {
+  if (n < 0) return fail("scd_cast_bf16: bad size");
+  if (n == 0) return 0;
+  if (!in || !out) return fail("scd_cast_bf16: null pointer");
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+  scd::cast_f32_to_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(in, n, reinterpret_cast<__nv_bfloat16*>(out));
+  SCD_LAUNCH_CHECK("cast_f32_to_bf16_kernel");
+  return 0;
+}
+
+int scd_gather_rows_bf16(const scd_bf16_t* Wt, const int64_t* sel, int n_sel, int D, int64_t V, scd_bf16_t* out, scd_stream_t stream) {
+  if (n_sel < 0 || D <= 0) return fail("scd_gather_rows_bf16: bad shape");
+  if (n_sel == 0) return 0;
+  if (!Wt || !sel || !out) return fail("scd_gather_rows_bf16: null pointer");
+  scd::gather_rows_bf16_kernel<<<n_sel, 128, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(Wt),
+                                                                    reinterpret_cast<const long long*>(sel), n_sel, D, V,
+                                                                    reinterpret_cast<__nv_bfloat16*>(out));
+  SCD_LAUNCH_CHECK("gather_rows_bf16_kernel");
+  return 0;
+}
+
+size_t scd_name_topk_workspace_bytes(int64_t N, int64_t V, int k) {
+  NamePlan pl;
+  if (N <= 0 || V <= 0 || !plan_naming(N, V, k, &pl)) return 256;
+  return pl.bytes;
+}
+
+int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, int64_t V, float scale, int k, int want_softmax,
+                  int64_t idx_offset, float* vals, int64_t* idx, float* row_max, float* row_sumexp, void* ws, size_t ws_bytes,
+                  scd_stream_t stream) {
+  if (N < 0 || V <= 0 || D <= 0) return fail("scd_name_topk: bad shape N=%lld V=%lld D=%d", (long long)N, (long long)V, D);
+  if (D > scd::kNameMaxD || D % 8 != 0) return fail("scd_name_topk: D=%d unsupported (need D <= %d and D %% 8 == 0)", D, scd::kNameMaxD);
+  if (k < 1 || k > 8) return fail("scd_name_topk: k=%d unsupported (1..8)", k);
+  if (V >= (1ll << 31) || N >= (1ll << 31)) return fail("scd_name_topk: N or V exceeds the int32 tile-coordinate range");
+  if (!(scale > 0.f)) return fail("scd_name_topk: scale must be positive");
+  if (N == 0) return 0;
+  if (!X || !Wt || !vals || !idx || !ws) return fail("scd_name_topk: null pointer");
+  if (((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Wt)) & 15) != 0) return fail("scd_name_topk: X and Wt must be 16-byte aligned");
+  NamePlan pl;
+  if (!plan_naming(N, V, k, &pl)) return fail("scd_name_topk: planning failed");
+  if (ws_bytes < pl.bytes) return fail("scd_name_topk: workspace too small (%zu < %zu)", ws_bytes, pl.bytes);
+  cudaStream_t st = as_stream(stream);
+
+  CUtensorMap mx, mw;
+  if (int e = make_map_bf16(&mx, X, (uint64_t)N, (uint64_t)D, scd::kBlockM, scd::kAKBlock, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  if (int e = make_map_bf16(&mw, Wt, (uint64_t)V, (uint64_t)D, scd::kTileN / 2, scd::kBK, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  scd::NameParams p;
+  p.n_rows = N;
+  p.v_total = V;
+  p.n_vsplit = pl.n_vsplit;
+  p.tiles_per_chunk = pl.tiles_per_chunk;
+  p.n_row_blocks = pl.n_row_blocks;
+  p.num_kb = (D + scd::kAKBlock - 1) / scd::kAKBlock;
+  p.want_softmax = want_softmax ? 1 : 0;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.part_val = reinterpret_cast<float*>(w8 + pl.off_val);
+  p.part_idx = reinterpret_cast<int*>(w8 + pl.off_idx);
+  p.part_max = reinterpret_cast<float*>(w8 + pl.off_max);
+  p.part_sum = reinterpret_cast<float*>(w8 + pl.off_sum);
+
+  int e = 0;
+  if (pl.kt == 1) e = launch_name_topk<1>(mx, mw, p, pl.n_pairs, st);
+  else if (pl.kt == 5) e = launch_name_topk<5>(mx, mw, p, pl.n_pairs, st);
+  else e = launch_name_topk<8>(mx, mw, p, pl.n_pairs, st);
+  if (e) return e;
+
+  const bool stats = want_softmax || row_max;
+  scd::topk_merge_kernel<int, false><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(
+      p.part_val, p.part_idx, stats ? p.part_max : nullptr, stats ? p.part_sum : nullptr, pl.n_vsplit, N, pl.kt, k, scale,
+      want_softmax ? 1 : 0, idx_offset, vals, reinterpret_cast<long long*>(idx), row_max, row_sumexp);
+  SCD_LAUNCH_CHECK("topk_merge_kernel");
+  return 0;
+}
+
+int scd_topk_merge(const float* part_vals, const int64_t* part_idx, const float* part_max, const float* part_sum, int parts,
+                   int64_t N, int k, float scale, int want_softmax, float* vals, int64_t* idx, scd_stream_t stream) {
+  if (parts < 1 || N < 0 || k < 1 || k > 8) return fail("scd_topk_merge: bad arguments parts=%d N=%lld k=%d", parts, (long long)N, k);
+  if (N == 0) return 0;
+  if (!part_vals || !part_idx || !vals || !idx) return fail("scd_topk_merge: null pointer");
+  if (want_softmax && (!part_max || !part_sum)) return fail("scd_topk_merge: softmax needs per-part row_max / row_sumexp");
+  scd::topk_merge_kernel<long long, true><<<(unsigned)((N + 127) / 128), 128, 0, as_stream(stream)>>>(
+      part_vals, reinterpret_cast<const long long*>(part_idx), want_softmax ? part_max : nullptr, want_softmax ? part_sum : nullptr,
+      parts, N, k, k, scale, want_softmax ? 1 : 0, 0, vals, reinterpret_cast<long long*>(idx), nullptr, nullptr);
+  SCD_LAUNCH_CHECK("topk_merge_kernel<shards>");
+  return 0;
+}
+
+// workspace layout (ints): counts[K] | offsets[K+1] | cursor[K] | order[N]
+size_t scd_vote_workspace_bytes(int64_t N, int K) {
+  return align_up((size_t)(3 * (size_t)K + 1 + (size_t)std::max<int64_t>(N, 0)) * sizeof(int), 256) + 256;
+}
+
+int scd_vote(const int64_t* topk_idx, int k_total, int k_used, const int64_t* cluster_of_row, int64_t N, int K,
+             const int64_t* excluded, int n_excluded, int M, int64_t* out_names, int32_t* out_counts, int32_t* out_distinct,
+             int32_t* out_rows, int32_t* overflow, void* ws, size_t ws_bytes, scd_stream_t stream) {
+  if (N < 0 || K <= 0 || k_total <= 0 || k_used <= 0 || k_used > k_total || M <= 0) return fail("scd_vote: bad arguments");
+  if (N * (int64_t)k_used >= (1ll << 32)) return fail("scd_vote: N * k_used exceeds the 32-bit position range");
+  if (K * sizeof(int) > 48 * 1024) return fail("scd_vote: K=%d too large", K);
+  if (!topk_idx || !cluster_of_row || !out_names || !out_counts || !out_distinct || !out_rows || !overflow || !ws) return fail("scd_vote: null pointer");
+  if (n_excluded > 0 && !excluded) return fail("scd_vote: excluded list is null");
+  if (ws_bytes < scd_vote_workspace_bytes(N, K)) return fail("scd_vote: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  int* counts = reinterpret_cast<int*>(ws);
+  int* offsets = counts + K;
+  int* cursor = offsets + K + 1;
+  int* order = cursor + K;
+  if (int e = sort_rows_by_label(cluster_of_row, N, K, counts, offsets, cursor, order, st)) return e;
+  SCD_CUDA(cudaMemcpyAsync(out_rows, counts, sizeof(int) * (size_t)K, cudaMemcpyDeviceToDevice, st));
+  SCD_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), st));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SCD_CUDA(cudaFuncSetAttribute(scd::vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scd::kVoteSmemBytes));
+    attr_set = true;
+  }
+  scd::vote_kernel<<<K, scd::kVoteThreads, scd::kVoteSmemBytes, st>>>(
+      reinterpret_cast<const long long*>(topk_idx), k_total, k_used, order, offsets, K, reinterpret_cast<const long long*>(excluded),
+      n_excluded, M, reinterpret_cast<long long*>(out_names), out_counts, out_distinct, overflow);
+  SCD_LAUNCH_CHECK("vote_kernel");
+  return 0;
+}
+
+}  // extern "C"

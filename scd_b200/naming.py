@@ -1,0 +1,294 @@
+"""Image x vocabulary scoring, per-image top-k, per-cluster voting, name assignment and
+re-assignment - the reference's inline naming code as functions over ``libscd_b200.so``.
+
+Reference call sites (paths relative to the reference checkout):
+  * scoring + top-k      ``main_unsup.py:504-531`` (softmax), ``main_ptsup.py:526-545`` (raw ``100*cos``)
+  * whole-vocab argmax   ``main_ptsup.py:78-99`` ``get_clip_preds_fast``
+  * top-k accuracy       ``local_utils/clip_lang_util.py:151-154`` ``accuracy``
+  * vote                 ``main_unsup.py:572-586``, ``main_ptsup.py:636-648``
+  * assign_name          ``local_utils/clip_lang_util.py:156-180`` (+ Hungarian ``gcd/project_utils/cluster_utils.py:234``)
+  * re-assignment        ``main_unsup.py:601-614``, ``main_ptsup.py:668-676``
+The de-facto signatures are kept: features ``[n, D]`` (tensor or ndarray) and ``zeroshot_weights [D, V]``
+in, ``(values [n, k], indices [n, k] int64)`` / ``LongTensor[n]`` / ``(ind, w)`` out.
+
+The contraction runs on the tcgen05 tensor cores in bf16 with fp32 accumulation (upstream CLIP on CUDA
+is fp16 end to end): features and vocabulary are rounded to bf16 once, the N x V logits never reach HBM.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes
+from collections import Counter
+
+import numpy as np
+import torch
+
+from . import _lib
+
+SCALE = 100.0          # the reference's logit scale (``100. *``)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError('scd_b200 needs a CUDA device (there is no CPU fallback)')
+
+
+def _feats_bf16(feats) -> torch.Tensor:
+    """[n, D] bf16 contiguous on the device (ndarray inputs are uploaded like ``main_unsup.py:522``)."""
+    _require_cuda()
+    if not torch.is_tensor(feats):
+        feats = torch.from_numpy(np.ascontiguousarray(feats))
+    feats = feats.to('cuda', non_blocking=True)
+    if feats.dtype == torch.bfloat16:
+        return feats.contiguous()
+    f32 = feats.to(torch.float32).contiguous()
+    out = torch.empty(f32.shape, dtype=torch.bfloat16, device=f32.device)
+    if f32.numel():
+        lib = _lib.load()
+        _lib.check(lib.scd_cast_bf16(f32.data_ptr(), f32.numel(), out.data_ptr(), _stream()), 'scd_cast_bf16')
+    return out
+
+
+class Vocabulary:
+    """``zeroshot_weights [D, V]`` (V contiguous, ``clip_lang_util.py:107``) re-laid out once as the K-major
+    bf16 operand ``Wt [V, D]``.  ``col_offset`` is the global index of column 0 when this rank holds a
+    column shard of a larger vocabulary."""
+
+    def __init__(self, zeroshot_weights, col_offset: int = 0):
+        _require_cuda()
+        W = zeroshot_weights if torch.is_tensor(zeroshot_weights) else torch.from_numpy(np.asarray(zeroshot_weights))
+        if W.dim() != 2:
+            raise ValueError('zeroshot_weights must be [D, V]')
+        W = W.to('cuda')
+        if W.dtype not in (torch.float32, torch.bfloat16):
+            W = W.to(torch.float32)
+        if W.stride(1) != 1:
+            W = W.contiguous()
+        self.D, self.V = int(W.shape[0]), int(W.shape[1])
+        self.col_offset = int(col_offset)
+        self.Wt = torch.empty(self.V, self.D, dtype=torch.bfloat16, device=W.device)
+        if self.V:
+            lib = _lib.load()
+            _lib.check(lib.scd_vocab_prepare(W.data_ptr(), int(W.dtype == torch.bfloat16), self.D, self.V, W.stride(0),
+                                             self.Wt.data_ptr(), _stream()), 'scd_vocab_prepare')
+
+    @classmethod
+    def from_rows(cls, Wt: torch.Tensor, col_offset: int = 0):
+        """Wrap an already K-major ``[V, D]`` bf16 tensor (e.g. gathered voted columns)."""
+        self = cls.__new__(cls)
+        self.Wt = Wt.contiguous()
+        self.V, self.D = int(Wt.shape[0]), int(Wt.shape[1])
+        self.col_offset = int(col_offset)
+        return self
+
+    def select(self, name_idx) -> 'Vocabulary':
+        """The ``[D, K]`` stack of voted columns (``main_unsup.py:601-602``) as a K-row vocabulary."""
+        sel = torch.as_tensor(np.asarray(name_idx, dtype=np.int64), device=self.Wt.device)
+        out = torch.empty(sel.numel(), self.D, dtype=torch.bfloat16, device=self.Wt.device)
+        if sel.numel():
+            lib = _lib.load()
+            _lib.check(lib.scd_gather_rows_bf16(self.Wt.data_ptr(), sel.data_ptr(), sel.numel(), self.D, self.V,
+                                                out.data_ptr(), _stream()), 'scd_gather_rows_bf16')
+        return Vocabulary.from_rows(out)
+
+
+def _as_vocab(w) -> Vocabulary:
+    return w if isinstance(w, Vocabulary) else Vocabulary(w)
+
+
+def name_topk_raw(feats_bf16: torch.Tensor, vocab: Vocabulary, k: int, softmax: bool, scale: float = SCALE,
+                  want_stats: bool = False):
+    """One launch of the fused scoring/top-k kernel on device-resident operands."""
+    n = int(feats_bf16.shape[0])
+    dev = feats_bf16.device
+    vals = torch.empty(n, k, dtype=torch.float32, device=dev)
+    idx = torch.empty(n, k, dtype=torch.int64, device=dev)
+    rmax = torch.empty(n, dtype=torch.float32, device=dev) if want_stats else None
+    rsum = torch.empty(n, dtype=torch.float32, device=dev) if want_stats else None
+    if n == 0:
+        return vals, idx, rmax, rsum
+    if int(feats_bf16.shape[1]) != vocab.D:
+        raise ValueError(f'feature width {int(feats_bf16.shape[1])} != vocabulary width {vocab.D}')
+    lib = _lib.load()
+    ws = torch.empty(lib.scd_name_topk_workspace_bytes(n, vocab.V, k), dtype=torch.uint8, device=dev)
+    _lib.check(lib.scd_name_topk(feats_bf16.data_ptr(), n, vocab.D, vocab.Wt.data_ptr(), vocab.V, float(scale), int(k),
+                                 int(bool(softmax)), vocab.col_offset, vals.data_ptr(), idx.data_ptr(),
+                                 _lib.ptr(rmax), _lib.ptr(rsum), ws.data_ptr(), ws.numel(), _stream()), 'scd_name_topk')
+    return vals, idx, rmax, rsum
+
+
+def score_topk(feats, zeroshot_weights, k: int = 5, softmax: bool = False, scale: float = SCALE):
+    """``logits = 100. * feats @ zeroshot_weights`` [+ ``F.softmax``] ``.topk(k, 1, True, True)``
+    (``main_unsup.py:519-529`` with ``softmax=True``; ``main_ptsup.py:538-543`` with ``softmax=False``).
+    Returns ``(values [n,k] fp32, indices [n,k] int64)``, largest first, ties -> lower index."""
+    vocab = _as_vocab(zeroshot_weights)
+    vals, idx, _, _ = name_topk_raw(_feats_bf16(feats), vocab, k, softmax, scale)
+    return vals, idx
+
+
+def clip_preds(feats, zeroshot_weights) -> torch.Tensor:
+    """``get_clip_preds_fast`` (``main_ptsup.py:78-99``) without the target bookkeeping: ``argmax`` over the
+    whole vocabulary, ``LongTensor[n]`` on the device."""
+    _, idx = score_topk(feats, zeroshot_weights, k=1)
+    return idx.view(-1)
+
+
+def accuracy(feats, zeroshot_weights, target, topk=(1,)):
+    """``accuracy(100. * feats @ W, target, topk)`` (``clip_lang_util.py:151-154``; used by
+    ``evaluate_semantic_acc_ub_lb`` ``main_ptsup.py:116-120``): number of rows whose target is in the top-k."""
+    _, idx = score_topk(feats, zeroshot_weights, k=max(topk))
+    tgt = torch.as_tensor(target, device=idx.device).view(-1, 1)
+    hit = idx.eq(tgt)
+    return [float(hit[:, :kk].any(dim=1).sum().item()) for kk in topk]
+
+
+def reassign(feats, zeroshot_weights, cand_name_idx) -> np.ndarray:
+    """``argmax(100. * feats @ W[:, cand], -1)`` -> NumPy int64 (``main_unsup.py:601-614`` /
+    ``main_ptsup.py:668-676``); positions index ``cand_name_idx``."""
+    vocab = _as_vocab(zeroshot_weights)
+    sel = vocab.select(cand_name_idx)
+    _, idx = score_topk(feats, sel, k=1)
+    return idx.view(-1).cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------- voting
+def vote_device(name_idx_topk: torch.Tensor, cluster_of_row, n_clusters: int, top_k: int, num_common: int,
+                known_name_idx=None):
+    """Device vote: per cluster the ``num_common`` most common names of ``name_idx_topk[rows, :top_k]``
+    (Python ``Counter.most_common`` order).  Returns device tensors
+    ``(names [K,M] int64 (-1 padded), counts [K,M] int32, distinct [K] int32, rows [K] int32)``."""
+    _require_cuda()
+    idx = name_idx_topk.to('cuda').to(torch.int64).contiguous()
+    cl = torch.as_tensor(cluster_of_row).to('cuda').to(torch.int64).contiguous()
+    n, kt = int(idx.shape[0]), int(idx.shape[1])
+    dev = idx.device
+    K, M = int(n_clusters), int(num_common)
+    names = torch.empty(K, M, dtype=torch.int64, device=dev)
+    counts = torch.empty(K, M, dtype=torch.int32, device=dev)
+    distinct = torch.empty(K, dtype=torch.int32, device=dev)
+    rows = torch.empty(K, dtype=torch.int32, device=dev)
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    excl = None
+    if known_name_idx is not None and len(known_name_idx):
+        excl = torch.as_tensor(np.asarray(list(known_name_idx), dtype=np.int64), device=dev)
+    lib = _lib.load()
+    ws = torch.empty(lib.scd_vote_workspace_bytes(n, K), dtype=torch.uint8, device=dev)
+    _lib.check(lib.scd_vote(idx.data_ptr(), kt, int(top_k), cl.data_ptr(), n, K, _lib.ptr(excl),
+                            0 if excl is None else int(excl.numel()), M, names.data_ptr(), counts.data_ptr(),
+                            distinct.data_ptr(), rows.data_ptr(), overflow.data_ptr(), ws.data_ptr(), ws.numel(),
+                            _stream()), 'scd_vote')
+    return names, counts, distinct, rows, overflow
+
+
+def vote(name_idx_topk, u_preds, cluster_ids, top_k: int, num_common: int, known_name_idx=None):
+    """``cluster_to_counter`` of ``main_unsup.py:575-577`` / ``main_ptsup.py:636-638``, truncated to each
+    cluster's ``num_common`` most common names (all the loop ever reads: ``most_common(num_common_vote)``
+    :582 and ``most_common(num_common)`` in ``assign_name`` with ``num_common <= num_common_vote``).
+    Counters are built in most-common order, so ``Counter.most_common(m)`` returns exactly what the
+    reference's full Counter returns for any ``m <= num_common``."""
+    cluster_ids = [int(c) for c in cluster_ids]
+    K = (max(cluster_ids) + 1) if cluster_ids else 1
+    preds = np.asarray(u_preds)
+    if preds.size and (preds.max() >= K):
+        K = int(preds.max()) + 1
+    names, counts, _, _, overflow = vote_device(name_idx_topk, preds, K, top_k, num_common, known_name_idx)
+    names_h, counts_h, ovf = names.cpu().numpy(), counts.cpu().numpy(), int(overflow.item())
+    if ovf:
+        raise RuntimeError('scd_vote: a cluster has more distinct names than the 16384-slot table')
+    out = {}
+    for c in cluster_ids:
+        ctr = Counter()
+        for name, cnt in zip(names_h[c], counts_h[c]):
+            if name < 0:
+                break
+            ctr[np.int64(name)] = int(cnt)
+        out[c] = ctr
+    return out
+
+
+def voted_candidates(cluster_to_counter, cluster_ids, num_common_vote: int):
+    """``main_unsup.py:579-586``: union of the clusters' ``most_common(num_common_vote)`` names in CPython
+    ``list(set(...))`` order (that order fixes the columns of ``w`` and so the Hungarian tie-breaks)."""
+    names = []
+    for i in cluster_ids:
+        for name, _cnt in cluster_to_counter[i].most_common(num_common_vote):
+            names += [name]
+    return list(set(names))
+
+
+def linear_assignment(cost) -> np.ndarray:
+    """``gcd/project_utils/cluster_utils.py:234``: Munkres with the reference's tie-breaking (host C++)."""
+    cost = np.ascontiguousarray(np.atleast_2d(cost), dtype=np.int64)
+    r, c = cost.shape
+    out = np.zeros((min(r, c), 2), dtype=np.int64)
+    n = ctypes.c_int(0)
+    lib = _lib.load()
+    rc = lib.scd_linear_assignment(cost.ctypes.data, r, c, out.ctypes.data, ctypes.byref(n))
+    if rc != 0:
+        raise RuntimeError('scd_linear_assignment failed')
+    return out[:n.value].astype(int)
+
+
+def assign_name(unique_name_idx, cluster_to_counter, num_common=4):
+    """``local_utils/clip_lang_util.py:156-180`` - same signature and return ``(ind, w)``."""
+    col_of = {name: j for j, name in enumerate(unique_name_idx)}
+    clusters = list(cluster_to_counter.keys())
+    dim = max(len(unique_name_idx), len(clusters))
+    w = np.zeros((dim, dim), dtype=int)
+    for row, cid in enumerate(clusters):
+        for name, cnt in cluster_to_counter[cid].most_common(num_common):
+            w[row, col_of[name]] += cnt
+    ind = linear_assignment(w.max() - w)
+    return ind, w
+
+
+def naming_loop_unsup(name_idx_topk, u_preds, clip_u_feats, zeroshot_weights, n_cluster, top_k=5,
+                      num_common_vote=20, num_common_linear=4, max_rounds=50):
+    """The iterative voting loop of ``main_unsup.py:568-614`` (names are vocabulary indices).  Returns the
+    per-round trace ``[{voted, u_preds, n_unique}]``; the last entry is the converged naming."""
+    vocab = _as_vocab(zeroshot_weights)
+    feats = _feats_bf16(clip_u_feats)
+    u_preds = np.asarray(u_preds)
+    cur, prev, trace = [-1], [-2], []
+    while set(cur) != set(prev) and len(trace) < max_rounds:
+        cluster_ids = list(set(u_preds))                                            # :573
+        c2c = vote(name_idx_topk, u_preds, cluster_ids, top_k, num_common_vote)     # :575-577
+        uniq = voted_candidates(c2c, cluster_ids, num_common_vote)                  # :579-586
+        ind, _w = assign_name(uniq, c2c, num_common=num_common_linear)              # :588
+        prev = copy.deepcopy(cur)
+        cur = [int(uniq[x[1]]) for x in ind[:n_cluster]]                            # :594
+        u_preds = reassign(feats, vocab, cur)                                       # :601-614
+        trace.append(dict(voted=list(cur), u_preds=u_preds.copy(), n_unique=len(uniq)))
+    return trace
+
+
+def naming_loop_ptsup(name_idx_topk, all_preds, mask_lab, clip_u_feats, zeroshot_weights, lab_name_idx, n_cluster,
+                      top_k=5, num_common_vote=20, num_common_linear=4, max_rounds=50):
+    """``main_ptsup.py:588-676`` including its index-space quirk (from round 2 ``unlab_cluster_idx`` /
+    ``known_name_idx`` are positions in ``cand_names`` while ``name_idx_topk`` holds vocabulary indices)."""
+    vocab = _as_vocab(zeroshot_weights)
+    feats = _feats_bf16(clip_u_feats)
+    all_preds, mask_lab = np.asarray(all_preds), np.asarray(mask_lab)
+    u_preds, l_preds = all_preds[~mask_lab], all_preds[mask_lab]                    # :592-593
+    lab_names = list(lab_name_idx)
+    num_unlab = n_cluster - len(lab_names)                                          # :602
+    known = list(lab_names)                                                         # :603
+    unlab_clusters = list(set(set(all_preds)) - set(l_preds))                       # :625
+    cur, prev, trace = [-1], [-2], []
+    while set(cur) != set(prev) and len(trace) < max_rounds:
+        c2c = vote(name_idx_topk, u_preds, unlab_clusters, top_k, num_common_vote, known_name_idx=known)   # :636-638
+        uniq = voted_candidates(c2c, unlab_clusters, num_common_vote)               # :640-648
+        ind, _w = assign_name(uniq, c2c, num_common=num_common_linear)              # :649
+        prev = copy.deepcopy(cur)
+        cur = [int(uniq[x[1]]) for x in ind[:num_unlab]]                            # :655
+        cand = sorted(set(cur + lab_names))                                         # :657-659
+        lab_class_index = [cand.index(n) for n in lab_names]                        # :662
+        unlab_clusters = [cand.index(n) for n in list(set(cand) - set(lab_names))]  # :664
+        known = copy.deepcopy(lab_class_index)                                      # :666
+        u_preds = reassign(feats, vocab, cand)                                      # :668-676
+        trace.append(dict(voted=list(cur), cand=list(cand), u_preds=u_preds.copy(), n_unique=len(uniq)))
+    return trace

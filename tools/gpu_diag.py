@@ -1,0 +1,155 @@
+#!/usr/bin/env python
+"""Bring-up diagnostics for the GPU box: each step runs in its own subprocess (a device trap in one step
+must not take the others down) with a timeout, and everything is logged under gpurun_out/.
+Usage: python tools/gpu_diag.py [step ...]      (no args = all steps)"""
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, 'gpurun_out')
+
+
+def step_kmeans():
+    import torch
+    from oracle import kmeans_oracle
+    from scd_b200 import kmeans
+    torch.manual_seed(0)
+    for (n, d, k) in [(600, 64, 12), (1, 8, 1), (130, 20, 65), (1000, 768, 100), (257, 4, 3)]:
+        X = torch.randn(n, d); X = X / X.norm(dim=1, keepdim=True)
+        C = X[torch.randperm(n)[:k]].clone() if n >= k else torch.randn(k, d)
+        ref = kmeans_oracle.pairwise_distance(X, C, None)
+        got = kmeans.pairwise_distance(X.cuda(), C.cuda()).cpu()
+        lab_o, mind_o, in_o = kmeans_oracle.estep(X, C)
+        lab = kmeans.predict(X.cuda(), C.cuda()).cpu()
+        print(f'pd n={n} d={d} k={k}: max|err|={float((ref-got).abs().max()):.3e} labels_equal={bool(torch.equal(lab, lab_o))}'
+              f' mismatches={int((lab!=lab_o).sum())}')
+        cen_o = kmeans_oracle.mstep(X, lab_o, C.clone())
+        ms = kmeans._MStep(n, d, k, 'cuda')
+        ms.sums_counts(X.cuda(), lab_o.cuda())
+        cn = torch.empty(k, d, device='cuda')
+        ms.finalize(C.cuda(), cn)
+        err = (cn.cpu() - cen_o)
+        both_nan = torch.isnan(cn.cpu()) & torch.isnan(cen_o)
+        err[both_nan] = 0
+        sh_o = float(kmeans_oracle.center_shift(cen_o, C))
+        print(f'   mstep max|err|={float(err.abs().max()):.3e} counts_ok={bool(torch.equal(ms.counts.cpu().long(), torch.bincount(lab_o, minlength=k)))}'
+              f' shift={float(ms.shift.item()):.6f} oracle_shift={sh_o:.6f}')
+    torch.cuda.synchronize()
+
+
+def _naming_case(n, v, d, k, softmax=False, verbose=False):
+    import torch
+    from scd_b200 import naming
+    g = torch.Generator().manual_seed(n * 7 + v)
+    X = torch.randn(n, d, generator=g); X = (X / X.norm(dim=1, keepdim=True)).bfloat16()
+    W = torch.randn(v, d, generator=g); W = (W / W.norm(dim=1, keepdim=True)).bfloat16()
+    Xd, Wd = X.cuda(), W.cuda()
+    logits = 100. * (Xd.float() @ Wd.float().t())
+    if softmax:
+        logits = torch.softmax(logits, dim=1)
+    kk = min(k, v)
+    rv, ri = logits.topk(kk, 1, True, True)
+    vocab = naming.Vocabulary(Wd.float().t().contiguous())
+    vals, idx, _, _ = naming.name_topk_raw(Xd, vocab, k, softmax)
+    torch.cuda.synchronize()
+    vals, idx = vals[:, :kk], idx[:, :kk]
+    verr = float((vals - rv).abs().max())
+    agree = float((idx == ri).float().mean())
+    print(f'naming n={n} v={v} d={d} k={k} softmax={softmax}: max|val err|={verr:.3e} idx agree={agree:.5f}')
+    if verbose and (agree < 0.999 or verr > 1e-2):
+        bad_rows = ((idx != ri).any(dim=1)).nonzero().view(-1)
+        print('   bad rows:', bad_rows[:40].tolist(), 'count', int(bad_rows.numel()))
+        for r in bad_rows[:4].tolist():
+            print('   row', r, 'got', idx[r].tolist(), [round(x, 3) for x in vals[r].tolist()], 'want', ri[r].tolist(), [round(x, 3) for x in rv[r].tolist()])
+    return verr, agree
+
+
+def step_naming_tiny():
+    _naming_case(256, 256, 64, 5, verbose=True)
+    _naming_case(256, 256, 64, 1, verbose=True)
+    _naming_case(128, 512, 128, 5, verbose=True)
+    _naming_case(256, 256, 768, 5, verbose=True)
+
+
+def step_naming_shapes():
+    for (n, v, d, k) in [(700, 300, 64, 5), (2048, 300, 64, 5), (2500, 1000, 64, 8), (1, 1, 64, 1), (300, 5000, 768, 5),
+                         (1000, 3000, 768, 5), (513, 257, 72, 2), (100, 255, 768, 3), (5000, 21000, 768, 5)]:
+        _naming_case(n, v, d, k, verbose=True)
+    _naming_case(1000, 3000, 768, 5, softmax=True, verbose=True)
+    _naming_case(300, 5000, 64, 5, softmax=True, verbose=True)
+
+
+def step_vote():
+    import numpy as np
+    import torch
+    from oracle import naming_oracle
+    from scd_b200 import naming
+    g = torch.Generator().manual_seed(3)
+    n, k, v = 5000, 17, 400
+    idx = torch.randint(0, v, (n, 5), generator=g)
+    idx[:, 0] = torch.randint(0, 30, (n,), generator=g)
+    preds = torch.randint(0, k, (n,), generator=g).numpy()
+    for known in (None, [1, 2, 3, 7]):
+        co = naming_oracle.vote(idx, preds, list(range(k)), 5, known_name_idx=known)
+        cg = naming.vote(idx, preds, list(range(k)), 5, 20, known_name_idx=known)
+        bad = sum([(int(a), int(b)) for a, b in cg[c].most_common(20)] != [(int(a), int(b)) for a, b in co[c].most_common(20)] for c in range(k))
+        print(f'vote known={known}: clusters differing = {bad} / {k}')
+
+
+def step_naming_time():
+    import torch
+    from scd_b200 import naming
+    n, v, d = 127000, 21000, 768
+    X = torch.randn(n, d, device='cuda'); X = (X / X.norm(dim=1, keepdim=True)).bfloat16()
+    W = torch.randn(v, d, device='cuda'); W = (W / W.norm(dim=1, keepdim=True)).bfloat16()
+    vocab = naming.Vocabulary.from_rows(W)
+    for _ in range(2):
+        naming.name_topk_raw(X, vocab, 5, False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        vals, idx, _, _ = naming.name_topk_raw(X, vocab, 5, False)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f'name_topk C2: {ms:.3f} ms -> {2*n*v*d/ms/1e9:.1f} TFLOP/s')
+    # check a row sample against torch
+    rows = torch.randperm(n, device='cuda')[:2048]
+    ref = (100. * (X[rows].float() @ W.float().t())).topk(5, 1, True, True)
+    print('   sample idx agree', float((idx[rows] == ref[1]).float().mean()), 'max val err', float((vals[rows] - ref[0]).abs().max()))
+    from scd_b200 import kmeans
+    Xf = torch.randn(n, d, device='cuda'); Xf = Xf / Xf.norm(dim=1, keepdim=True)
+    C = Xf[:100].clone()
+    labels = torch.empty(n, dtype=torch.int64, device='cuda'); acc = torch.zeros(1, dtype=torch.float64, device='cuda')
+    ms_ = kmeans._MStep(n, d, 100, 'cuda'); cn = torch.empty_like(C)
+    for name, fn in (('estep', lambda: kmeans._estep(Xf, C, labels, acc)), ('mstep', lambda: (ms_.sums_counts(Xf, labels), ms_.finalize(C, cn)))):
+        fn(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        print(f'{name} C2: {e0.elapsed_time(e1)/5:.3f} ms')
+
+
+STEPS = ['kmeans', 'naming_tiny', 'naming_shapes', 'vote', 'naming_time']
+
+if __name__ == '__main__':
+    if len(sys.argv) > 2 and sys.argv[1] == '--run':
+        globals()['step_' + sys.argv[2]]()
+        sys.exit(0)
+    os.makedirs(OUT, exist_ok=True)
+    steps = sys.argv[1:] or STEPS
+    for s in steps:
+        t0 = time.time()
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), '--run', s], capture_output=True, text=True, timeout=240)
+            rc, out = p.returncode, p.stdout + '\n--- stderr ---\n' + p.stderr[-6000:]
+        except subprocess.TimeoutExpired as e:
+            rc, out = -999, 'TIMEOUT\n' + str(e.stdout)[-3000:] + str(e.stderr)[-3000:]
+        with open(os.path.join(OUT, f'diag_{s}.txt'), 'w') as f:
+            f.write(out)
+        print(f'===== {s}: rc={rc} ({time.time()-t0:.1f}s)')
+        print(out[-3500:])
