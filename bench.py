@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the SCD naming round (BASELINE.json metric: ms per naming round = one k-means iteration
++ full-vocabulary scoring with per-image top-k + per-cluster vote).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C2]
+
+* default arm: the B200 path.  `value` = ms per round with all inputs resident in HBM (CUDA events, max
+  over ranks); `e2e` = the same round through the public Python API with HOST (pinned) buffers, H2D/D2H
+  inside the timed region; `roofline` = the dominant kernel (fused scoring/top-k, tensor-core bound)
+  against MEASURED_PEAKS.json; `cpu_baseline` = the oracle (a port of the reference's PyTorch path) timed on
+  this box's host cores on a bounded row sample (N=1 / rank 0 only).
+* N > 1 (launched by torch.distributed.run, one rank per GPU): STRONG scaling of the same workload - rows
+  block-sharded for k-means (one packed NCCL all-reduce per iteration), vocabulary column-sharded for naming
+  (local fused top-k, all-gather, k-way merge), vote replicated.
+* --impl reference: the reference's own CPU implementation of the path (the oracle port - the reference is
+  Python/PyTorch, there is nothing to compile into oracle/_ref) with all host threads, on a bounded sample of
+  the same workload, extrapolated linearly in rows.  Rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = 'ms per naming round (k-means iter + vocab top-k + vote)'
+CPU_SAMPLE_ROWS = 8192
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p.get('hbm_gbs', 6650.0), tflops=p.get('bf16_tflops', 1590.0),
+                    tflops_sustained=p.get('bf16_tflops_sustained', 1400.0), source='measured')
+    return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source='fallback')
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU while the timed region runs (pynvml, 50 ms period)."""
+
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap',
+               0x80: 'hw_power_brake_slowdown'}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag = index, threading.Event()
+        self.sm, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                bits = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag.set()
+        if self.ok and self.is_alive():
+            self.join(timeout=1.0)
+        return dict(sm_mhz=(float(np.median(self.sm)) if self.sm else None), sm_max_mhz=self.max_mhz,
+                    reasons=sorted(self.reasons), samples=len(self.sm))
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+    if vis:
+        try:
+            return int(vis.split(',')[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+_CPU_DATA = {}
+
+
+def cpu_round_ms(cfg, sample_rows, threads, repeats=2):
+    """One naming round of the reference's CPU path (oracle port) on `sample_rows` rows of the workload,
+    extrapolated linearly to cfg.n rows.  Returns (ms_per_round_full, detail dict)."""
+    from oracle import kmeans_oracle, naming_oracle
+    from scd_b200 import synth
+    torch.set_num_threads(threads)
+    n = min(sample_rows, cfg.n)
+    if (cfg.name, n) not in _CPU_DATA:
+        _CPU_DATA[(cfg.name, n)] = synth.make(cfg, n_rows=n)
+    data = _CPU_DATA[(cfg.name, n)]
+    X, Xc, W, C0 = data['X'], data['Xc'], data['W'], data['C0']
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        labels, _, _ = kmeans_oracle.estep(X, C0, 1024)                     # pairwise_distance(X, C, 1024) + torch.min
+        kmeans_oracle.mstep(X, labels, C0.clone())                          # the :61-64 loop
+        t1 = time.perf_counter()
+        idx, _ = naming_oracle.score_topk(Xc, W, 5, variant='ptsup')        # main_ptsup.py:526-545 restated
+        t2 = time.perf_counter()
+        c2c = naming_oracle.vote(idx, labels.numpy(), list(range(cfg.k)), 5)
+        naming_oracle.voted_candidates(c2c, list(range(cfg.k)), 20)
+        t3 = time.perf_counter()
+        cur = dict(kmeans=t1 - t0, naming=t2 - t1, vote=t3 - t2, total=t3 - t0)
+        if best is None or cur['total'] < best['total']:
+            best = cur
+    scale = cfg.n / n
+    detail = {k: round(v * 1e3 * scale, 1) for k, v in best.items()}
+    return best['total'] * 1e3 * scale, detail, n
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class Round:
+    """Device-resident state of one rank and the launches of one naming round."""
+
+    def __init__(self, cfg, rank, world, group):
+        from scd_b200 import dist as sdist, kmeans, naming, synth
+        self.cfg, self.rank, self.world, self.group = cfg, rank, world, group
+        self.kmeans, self.naming, self.sdist = kmeans, naming, sdist
+        data = synth.make(cfg)
+        self.host = data
+        dev = torch.device('cuda')
+        self.row_lo, self.row_hi = sdist.shard_bounds(cfg.n, world, rank)
+        self.col_lo, self.col_hi = sdist.shard_bounds(cfg.v, world, rank)
+        # resident operands: my row shard of X (fp32), all rows of Xc (bf16), my column shard of the vocabulary
+        self.X = data['X'][self.row_lo:self.row_hi].to(dev).contiguous()
+        self.Xc = naming._feats_bf16(data['Xc'])
+        self.vocab = naming.Vocabulary(data['W'][:, self.col_lo:self.col_hi].to(dev), col_offset=self.col_lo)
+        self.C = data['C0'].to(dev).contiguous()
+        self.C_new = torch.empty_like(self.C)
+        n_local = self.X.shape[0]
+        self.labels = torch.empty(n_local, dtype=torch.int64, device=dev)
+        self.labels_all = torch.empty(cfg.n, dtype=torch.int64, device=dev) if world > 1 else self.labels
+        self.inertia = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.mstep = kmeans._MStep(n_local, synth.D, cfg.k, dev)
+        self.km = kmeans.K_Means(k=cfg.k, process_group=group if world > 1 else None)
+        self.launches_per_round = 0
+        self.ev_name = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        self.name_ms = []
+
+    def run(self, record_naming=False):
+        cfg, km, nm = self.cfg, self.kmeans, self.naming
+        launches = 0
+        # ---- k-means iteration: E-step, M-step sums, (all-reduce), divide + centre shift
+        self.inertia.zero_()
+        km._estep(self.X, self.C, self.labels, self.inertia); launches += 1
+        self.mstep.sums_counts(self.X, self.labels); launches += 4
+        counts_f = self.km._allreduce(self.mstep, self.inertia)
+        self.mstep.finalize(self.C, self.C_new, counts_f); launches += 2
+        # ---- full-vocabulary scoring + per-image top-5
+        if record_naming:
+            self.ev_name[0].record()
+        if self.world == 1:
+            vals, idx, _, _ = nm.name_topk_raw(self.Xc, self.vocab, 5, False); launches += 2
+        else:
+            vals, idx = self.sdist.sharded_score_topk(self.Xc, self.vocab, 5, False, self.group); launches += 3
+        if record_naming:
+            self.ev_name[1].record()
+        # ---- per-cluster vote (labels of all rows; replicated on every rank when sharded)
+        if self.world > 1:
+            import torch.distributed as dist
+            parts = [self.labels_all[lo:hi] for lo, hi in (self.sdist.shard_bounds(cfg.n, self.world, r) for r in range(self.world))]
+            dist.all_gather(parts, self.labels, group=self.group)
+        out = nm.vote_device(idx, self.labels_all, cfg.k, 5, 20); launches += 4
+        self.launches_per_round = launches
+        self.last = (vals, idx, out)
+        return out
+
+
+def e2e_round(cfg, host, vocab, pinned):
+    """One round through the public API from HOST buffers: H2D of the step's inputs, the round, D2H of the results."""
+    from scd_b200 import kmeans, naming
+    X = pinned['X'].to('cuda', non_blocking=True)
+    C = pinned['C0'].to('cuda', non_blocking=True)
+    Xc = pinned['Xc'].to('cuda', non_blocking=True)
+    km = kmeans.K_Means(k=cfg.k, max_iterations=1, n_init=1)
+    labels = torch.empty(cfg.n, dtype=torch.int64, device='cuda')
+    best_labels, inertia, centers, _ = km._lloyd(X, X, labels, 0, C)
+    vals, idx = naming.score_topk(Xc, vocab, k=5, softmax=False)
+    names, counts, distinct, rows, ovf = naming.vote_device(idx, best_labels, cfg.k, 5, 20)
+    res = [t.to('cpu', non_blocking=True) for t in (best_labels, centers, vals, idx, names, counts)]
+    torch.cuda.synchronize()
+    h2d = X.numel() * 4 + C.numel() * 4 + Xc.numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in res) + 16
+    return h2d, d2h
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='C2')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+
+    from scd_b200 import synth
+    cfg = synth.CONFIGS[args.config]
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    config = dict(workload=f'{cfg.name}: {cfg.n}x{synth.D} image features, K={cfg.k}, V={cfg.v} names, top-5, vote top-20',
+                  n=cfg.n, d=synth.D, k=cfg.k, v=cfg.v, topk=5, l2='inputs (585 MB features + 32 MB vocabulary) exceed the 126 MB L2',
+                  parallelism=('single GPU' if world == 1 else f'rows/{world} (k-means, all-reduce) x vocab/{world} (naming, all-gather + merge)'))
+
+    # -------------------------------------------------------------------------------- reference arm
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        vals = []
+        for s in range(max(args.steps, 1) + max(args.warmup, 0)):
+            ms, detail, n_s = cpu_round_ms(cfg, CPU_SAMPLE_ROWS, threads, repeats=1)
+            if s >= args.warmup:
+                vals.append(ms)
+        v = float(np.median(vals))
+        sample = f'{n_s} of {cfg.n} rows (all {cfg.k} centroids, all {cfg.v} names), time scaled linearly in rows'
+        print(json.dumps(dict(impl='reference', metric=METRIC, value=round(v, 1), unit='ms', n_gpus=args.gpus, steps=args.steps,
+                              warmup=args.warmup, ms_per_step=round(v, 1), higher_is_better=False, scaling='strong',
+                              vs_baseline=None, dtype='f32', data='synthetic', config=config,
+                              cpu_baseline=dict(value=round(v, 1), unit='ms', cores=threads, kind='port', sample=sample, split_ms=detail),
+                              e2e=dict(value=round(v, 1), unit='ms', h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return 0
+
+    # -------------------------------------------------------------------------------- B200 arm
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (the B200 path has no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        group = dist.group.WORLD
+    peaks = load_peaks()
+    rnd = Round(cfg, rank, world, group)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=group)
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        rnd.run()
+    barrier()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    name_evs = []
+    ev0.record()
+    for _ in range(args.steps):
+        rnd.run(record_naming=True)
+        name_evs.append(rnd.ev_name)
+        rnd.ev_name = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ev1.record()
+    barrier()
+    clocks = sampler.result()
+    ms_total = ev0.elapsed_time(ev1)
+    name_ms = float(np.mean([a.elapsed_time(b) for a, b in name_evs]))
+    t = torch.tensor([ms_total, name_ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    ms_per_step = float(t[0]) / args.steps
+    name_ms = float(t[1])
+
+    # roofline of the dominant kernel: fused scoring/top-k (tensor-core bound); algorithmic flops = 2*N*V*D / ranks
+    flops = 2.0 * cfg.n * (rnd.col_hi - rnd.col_lo) * synth.D
+    achieved = flops / (name_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get('name_topk_kernel_dram_bytes_per_launch')
+    roofline = dict(bound='tensor', kernel='name_topk_kernel<5> (+ topk_merge)', achieved=round(achieved, 1), peak=peaks['tflops'],
+                    unit='TFLOP/s', frac=round(achieved / peaks['tflops'], 4), traffic=traffic,
+                    peak_source=f"{peaks['source']} bf16 burst (MEASURED_PEAKS.json)", kernel_ms=round(name_ms, 4),
+                    flops_per_launch=flops)
+
+    e2e = None
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        pinned = {k: rnd.host[k].pin_memory() for k in ('X', 'Xc', 'C0')}
+        for _ in range(2):
+            h2d, d2h = e2e_round(cfg, rnd.host, rnd.vocab, pinned)
+        torch.cuda.synchronize()
+        n_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            h2d, d2h = e2e_round(cfg, rnd.host, rnd.vocab, pinned)
+        torch.cuda.synchronize()
+        e2e = dict(value=round((time.perf_counter() - t0) * 1e3 / n_e2e, 3), unit='ms', h2d_bytes_per_step=int(h2d),
+                   d2h_bytes_per_step=int(d2h), api='K_Means._lloyd(1 iter) + naming.score_topk + naming.vote_device from pinned host tensors')
+    elif world > 1:
+        e2e = dict(value=None, unit='ms', h2d_bytes_per_step=0, d2h_bytes_per_step=0, note='measured at N=1 only')
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, detail, n_s = cpu_round_ms(cfg, CPU_SAMPLE_ROWS, threads, repeats=2)
+        cpu_baseline = dict(value=round(v, 1), unit='ms', cores=threads, kind='port', split_ms=detail,
+                            sample=f'{n_s} of {cfg.n} rows (all {cfg.k} centroids, all {cfg.v} names), time scaled linearly in rows')
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=round(ms_per_step, 4), unit='ms', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=round(ms_per_step, 4), higher_is_better=False, scaling='strong', vs_baseline=None, dtype='bf16',
+                    data='synthetic', config=config, clocks=clocks, e2e=e2e, gpu_launches=rnd.launches_per_round * args.steps,
+                    roofline=roofline, cpu_baseline=cpu_baseline,
+                    split=dict(naming_ms=round(name_ms, 4), kmeans_vote_ms=round(ms_per_step - name_ms, 4)))
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

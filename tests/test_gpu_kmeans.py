@@ -1,0 +1,207 @@
+"""GPU parity: k-means E-step / M-step / fit / fit_mix through the C ABI against the oracle and the
+reference-generated golden fixtures.
+
+Tolerances (BASELINE.json north_star): centroids and distances within 1e-4 absolute (fp32 accumulate);
+assignments bit-exact wherever the top-1/top-2 distance margin exceeds TAU = 1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kmeans_oracle
+from scd_b200 import kmeans, synth
+
+pytestmark = pytest.mark.gpu
+TAU = 1e-5
+ATOL = 1e-4
+
+
+def _margin_mask(dist: torch.Tensor) -> torch.Tensor:
+    if dist.shape[1] < 2:
+        return torch.ones(dist.shape[0], dtype=torch.bool)
+    two = dist.topk(2, dim=1, largest=False).values
+    return (two[:, 1] - two[:, 0]) > TAU
+
+
+def _assert_labels(labels_gpu, X, C):
+    dist = kmeans_oracle.pairwise_distance(X, C, None)
+    want = dist.argmin(dim=1)
+    ok = _margin_mask(dist)
+    assert ok.float().mean() > 0.98
+    assert torch.equal(labels_gpu.cpu()[ok], want[ok])
+
+
+@pytest.mark.parametrize('n,d,k', [(600, 64, 12), (1, 8, 1), (130, 20, 65), (1000, 768, 100), (257, 4, 3), (4096, 768, 200)])
+def test_pairwise_distance_and_estep(n, d, k):
+    g = torch.Generator().manual_seed(n + d + k)
+    X = synth.unit_rows(torch.randn(n, d, generator=g))
+    C = synth.unit_rows(torch.randn(k, d, generator=g))
+    ref = kmeans_oracle.pairwise_distance(X, C, None)
+    got = kmeans.pairwise_distance(X.cuda(), C.cuda())
+    assert got.is_cuda and got.shape == (n, k)
+    assert torch.allclose(got.cpu(), ref, atol=ATOL, rtol=0)
+    got_b = kmeans.pairwise_distance(X.cuda(), C.cuda(), 1024)          # reference: batched result lives on the CPU
+    assert not got_b.is_cuda and torch.allclose(got_b, ref, atol=ATOL, rtol=0)
+    labels = torch.empty(n, dtype=torch.int64, device='cuda')
+    mind = torch.empty(n, dtype=torch.float32, device='cuda')
+    acc = torch.zeros(1, dtype=torch.float64, device='cuda')
+    kmeans._estep(X.cuda(), C.cuda(), labels, acc, mind)
+    _assert_labels(labels, X, C)
+    assert torch.allclose(mind.cpu(), ref.min(dim=1).values, atol=ATOL, rtol=0)
+    assert abs(acc.item() - ref.min(dim=1).values.double().sum().item()) < 1e-3
+    assert torch.equal(kmeans.predict(X.cuda(), C.cuda()), labels)
+
+
+def test_pairwise_distance_matches_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'kmeans_small.npz'))
+    got = kmeans.pairwise_distance(torch.from_numpy(g['X']).cuda(), torch.from_numpy(g['C0']).cuda(), 100)
+    assert np.allclose(got.numpy(), g['pd_b100'], atol=ATOL, rtol=0)
+    assert kmeans.pairwise_distance(torch.zeros(0, 64).cuda(), torch.from_numpy(g['C0']).cuda(), 10).shape == (0, 12)
+
+
+def test_estep_tie_and_nan_rules():
+    # duplicate centroids: ties go to the lowest index; a NaN centroid wins every row (torch.min semantics)
+    X = synth.unit_rows(torch.randn(300, 32, generator=torch.Generator().manual_seed(1)))
+    C = X[:6].clone(); C[4] = C[1]; C[5] = C[0]
+    lab = kmeans.predict(X.cuda(), C.cuda()).cpu()
+    want = kmeans_oracle.pairwise_distance(X, C, None).argmin(dim=1)
+    assert torch.equal(lab, want) and not ((lab == 4) | (lab == 5)).any()
+    C[3] = float('nan')
+    lab = kmeans.predict(X.cuda(), C.cuda()).cpu()
+    assert torch.equal(lab, torch.min(kmeans_oracle.pairwise_distance(X, C, None), dim=1)[1])
+    assert (lab == 3).all()
+
+
+@pytest.mark.parametrize('n,d,k', [(600, 64, 12), (5000, 768, 100), (257, 4, 3), (3000, 100, 1000), (1, 8, 2)])
+def test_mstep_matches_oracle(n, d, k):
+    g = torch.Generator().manual_seed(n * 3 + k)
+    X = torch.randn(n, d, generator=g)
+    labels = torch.randint(0, k, (n,), generator=g)
+    if k > 2:
+        labels[labels == 1] = 0                          # cluster 1 is empty -> NaN row
+    C0 = torch.randn(k, d, generator=g)
+    want = kmeans_oracle.mstep(X, labels, C0.clone())
+    ms = kmeans._MStep(n, d, k, 'cuda')
+    ms.sums_counts(X.cuda(), labels.cuda())
+    got = torch.empty(k, d, device='cuda')
+    ms.finalize(C0.cuda(), got)
+    got = got.cpu()
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.allclose(got, want, atol=ATOL, rtol=1e-5, equal_nan=True)
+    assert torch.equal(ms.counts.cpu().long(), torch.bincount(labels, minlength=k))
+    shift_want = kmeans_oracle.center_shift(want, C0)
+    if torch.isnan(shift_want):
+        assert torch.isnan(ms.shift.cpu()).all()
+    else:
+        assert abs(ms.shift.item() - shift_want.item()) < 1e-3 * max(1.0, shift_want.item())
+
+
+def test_mstep_ignores_unassigned_rows_and_is_permutation_invariant():
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(2000, 128, generator=g)
+    labels = torch.randint(-1, 7, (2000,), generator=g)
+    ms = kmeans._MStep(2000, 128, 7, 'cuda')
+    ms.sums_counts(X.cuda(), labels.cuda())
+    s1, c1 = ms.sums.clone(), ms.counts.clone()
+    perm = torch.randperm(2000, generator=g)
+    ms.sums_counts(X[perm].cuda(), labels[perm].cuda())
+    assert torch.equal(c1, ms.counts) and torch.allclose(s1, ms.sums, atol=1e-3)
+    keep = labels >= 0
+    assert torch.allclose(s1.sum(0).cpu(), X[keep].sum(0), atol=1e-3)
+    assert int(c1.sum()) == int(keep.sum())
+
+
+@pytest.mark.parametrize('init', ['random', 'first'])
+def test_fit_matches_reference_golden(golden_dir, init):
+    g = np.load(os.path.join(golden_dir, 'kmeans_small.npz'))
+    km = kmeans.K_Means(k=12, tolerance=1e-4, max_iterations=6, init=init, n_init=2, random_state=3, n_jobs=None,
+                        pairwise_batch_size=None)
+    km.fit(torch.from_numpy(g['X']).cuda())
+    assert km.labels_.is_cuda and km.labels_.dtype == torch.int64
+    assert np.array_equal(km.labels_.cpu().numpy(), g[f'fit_{init}_labels'])
+    assert np.allclose(km.cluster_centers_.cpu().numpy(), g[f'fit_{init}_centers'], atol=ATOL, rtol=0)
+    assert abs(float(km.inertia_) - float(g[f'fit_{init}_inertia'])) < 1e-3
+    assert km.n_iter_ == int(g[f'fit_{init}_n_iter'])
+
+
+def test_fit_empty_cluster_gives_nan_row_like_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'kmeans_empty_cluster.npz'))
+    km = kmeans.K_Means(k=5, max_iterations=1, init='first', n_init=1, random_state=0, pairwise_batch_size=None)
+    km.fit(torch.from_numpy(g['X']).cuda())
+    assert np.array_equal(km.labels_.cpu().numpy(), g['labels'])
+    got = km.cluster_centers_.cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(g['centers'])) and np.isnan(got).any()
+    assert np.allclose(got, g['centers'], atol=ATOL, rtol=0, equal_nan=True)
+
+
+def test_kpp_follows_the_oracle_draws():
+    """Same host RNG stream, same 'first cumulative >= r' rule: with well separated candidates the seeds
+    are the oracle's.  (Exact equality is not guaranteed in general: the selected index depends on
+    fp32 cumsum rounding, which differs even between the reference's own CPU and GPU runs.)"""
+    X, _ = synth.image_feats(400, 8, seed=9, d=64)
+    ko = kmeans_oracle.K_Means(k=8, pairwise_batch_size=None)
+    want = ko.kpp(X, k=8, random_state=5)
+    got = kmeans.K_Means(k=8).kpp(X.cuda(), k=8, random_state=5).cpu()
+    assert got.shape == want.shape
+    same = (got - want).abs().max(dim=1).values < 1e-6
+    assert same.float().mean() >= 0.75
+
+
+def test_fit_mix_matches_oracle_from_identical_seeds(golden_dir):
+    """fit_mix against the oracle with the k-means++ seeds forced to the oracle's (see test above for why)."""
+    g = np.load(os.path.join(golden_dir, 'kmeans_small.npz'))
+    u, l, lt = torch.from_numpy(g['u_feats']), torch.from_numpy(g['l_feats']), torch.from_numpy(g['l_targets'])
+    ko = kmeans_oracle.K_Means(k=12, tolerance=1e-4, max_iterations=10, init='k-means++', n_init=1, random_state=7,
+                               pairwise_batch_size=128)
+    seeds = []
+    orig = ko.kpp
+    ko.kpp = lambda *a, **kw: seeds.append(orig(*a, **kw)) or seeds[-1]
+    ko.fit_mix(u, l, lt)
+    km = kmeans.K_Means(k=12, tolerance=1e-4, max_iterations=10, init='k-means++', n_init=1, random_state=7,
+                        pairwise_batch_size=128, mode=None)
+    km.kpp = lambda *a, **kw: seeds[0].cuda()
+    km.fit_mix(u.cuda(), l.cuda(), lt.cuda())
+    assert np.array_equal(km.labels_.cpu().numpy(), ko.labels_.numpy())
+    assert np.allclose(km.cluster_centers_.cpu().numpy(), ko.cluster_centers_.numpy(), atol=ATOL, rtol=0)
+    assert abs(float(km.inertia_) - float(ko.inertia_)) < 1e-3
+    assert km.n_iter_ == ko.n_iter_ == len(lt)            # the reference's n_iter_ quirk
+    # labelled rows come first and keep their (remapped) class ids
+    assert np.array_equal(km.labels_.cpu().numpy()[:len(lt)], np.unique(lt.numpy(), return_inverse=True)[1])
+
+
+def test_blobs_demo_end_to_end(golden_dir):
+    """The reference's own demo (faster_mix_k_means_pytorch.py:221-249), float64 inputs, real k-means++."""
+    g = np.load(os.path.join(golden_dir, 'kmeans_blobs_demo.npz'))
+    km = kmeans.K_Means(k=4, init='k-means++', random_state=1, n_jobs=None, pairwise_batch_size=10)
+    km.fit_mix(torch.from_numpy(g['u_feats']), torch.from_numpy(g['l_feats']), torch.from_numpy(g['l_targets']))
+    assert not km.labels_.is_cuda                         # CPU tensors in -> CPU results out
+    assert np.array_equal(km.labels_.numpy(), g['labels'])
+    assert np.allclose(km.cluster_centers_.numpy(), g['centers'], atol=1e-3)
+    assert km.n_iter_ == int(g['n_iter'])
+
+
+def test_full_size_c2_properties():
+    """127k x 768, K=100 (BASELINE configs[1]): size-independent properties + an oracle check on a row sample."""
+    cfg = synth.CONFIGS['C2']
+    X, _ = synth.image_feats(cfg.n, cfg.k, cfg.seed)
+    C0 = synth.random_init_centers(X, cfg.k, cfg.seed)
+    Xd, Cd = X.cuda(), C0.cuda()
+    labels = torch.empty(cfg.n, dtype=torch.int64, device='cuda')
+    mind = torch.empty(cfg.n, dtype=torch.float32, device='cuda')
+    acc = torch.zeros(1, dtype=torch.float64, device='cuda')
+    kmeans._estep(Xd, Cd, labels, acc, mind)
+    assert abs(acc.item() - mind.double().sum().item()) < 1e-6 * cfg.n          # inertia == sum of minima
+    rows = torch.randperm(cfg.n, generator=torch.Generator().manual_seed(0))[:4096]
+    _assert_labels(labels[rows.cuda()], X[rows], C0)
+    full = kmeans.pairwise_distance(Xd[:8192], Cd)                             # E-step == argmin of the full matrix
+    assert torch.equal(full.argmin(dim=1), labels[:8192])
+    ms = kmeans._MStep(cfg.n, synth.D, cfg.k, 'cuda')
+    ms.sums_counts(Xd, labels)
+    assert int(ms.counts.sum()) == cfg.n
+    assert torch.equal(ms.counts.long(), torch.bincount(labels, minlength=cfg.k))
+    assert torch.allclose(ms.sums.sum(0).cpu(), X.double().sum(0).float(), atol=2e-2)   # column totals are preserved
+    cn = torch.empty_like(Cd)
+    ms.finalize(Cd, cn)
+    sub = labels.cpu() == 7
+    assert torch.allclose(cn[7].cpu(), X[sub].double().mean(0).float(), atol=ATOL)
