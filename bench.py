@@ -22,7 +22,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -47,46 +46,68 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source='fallback')
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons of one GPU while the timed region runs (pynvml, 50 ms period)."""
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU while the timed region runs: a background
+    `nvidia-smi -lms 100` process (the profiling recipe's clocks line) - a separate process, so the
+    queries never contend with this process's launch path (in-process NVML polling did: it doubled the
+    measured step time)."""
 
-    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap',
-               0x80: 'hw_power_brake_slowdown'}
+    FIELDS = ['clocks.sm', 'clocks.max.sm', 'power.draw', 'clocks_event_reasons.hw_slowdown',
+              'clocks_event_reasons.hw_thermal_slowdown', 'clocks_event_reasons.sw_thermal_slowdown',
+              'clocks_event_reasons.sw_power_cap']
 
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.stop_flag = index, threading.Event()
-        self.sm, self.reasons, self.max_mhz, self.ok = [], set(), None, False
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.ok = True
-        except Exception:
-            self.ok = False
-
-    def run(self):
-        if not self.ok:
+    def __init__(self, index, enabled=True):
+        self.proc, self.t_start, self.t_stop = None, None, None
+        if not enabled:
             return
-        while not self.stop_flag.is_set():
-            try:
-                self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                bits = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if bits & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.05)
+        try:
+            import subprocess
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=timestamp,' + ','.join(self.FIELDS),
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.35)           # let it print its first line before the region starts
+        except Exception:
+            self.proc = None
+
+    def start(self):
+        self.t_start = time.time()
 
     def result(self):
-        self.stop_flag.set()
-        if self.ok and self.is_alive():
-            self.join(timeout=1.0)
-        return dict(sm_mhz=(float(np.median(self.sm)) if self.sm else None), sm_max_mhz=self.max_mhz,
-                    reasons=sorted(self.reasons), samples=len(self.sm))
+        self.t_stop = time.time()
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            text, _ = self.proc.communicate(timeout=2)
+        except Exception:
+            self.proc.kill()
+            return out
+        import datetime
+        sm, reasons, mx, power = [], set(), None, []
+        for line in text.strip().splitlines():
+            parts = [x.strip() for x in line.split(',')]
+            if len(parts) != 1 + len(self.FIELDS):
+                continue
+            try:
+                ts = datetime.datetime.strptime(parts[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                clk, mxc = float(parts[1]), float(parts[2])
+            except Exception:
+                continue
+            mx = mxc
+            if self.t_start - 0.05 <= ts <= self.t_stop + 0.05:
+                sm.append(clk)
+                try:
+                    power.append(float(parts[3]))
+                except Exception:
+                    pass
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), parts[4:]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+        out.update(sm_mhz=(float(np.median(sm)) if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm),
+                   power_w_max=(max(power) if power else None))
+        return out
 
 
 def physical_gpu_index(local_rank):
@@ -212,12 +233,13 @@ def e2e_round(cfg, host, vocab, pinned):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default='C2')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-clocks', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
@@ -269,7 +291,8 @@ def main():
     for _ in range(args.warmup):
         rnd.run()
     barrier()
-    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler = ClockSampler(physical_gpu_index(local_rank), enabled=not args.no_clocks)
+    barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     name_evs = []

@@ -275,6 +275,18 @@ segment_sum_kernel(const float* __restrict__ X, const int* __restrict__ order, c
   flush(k);
 }
 
+// Shape-generic variant (any D, any alignment): one thread per (cluster, column), fixed summation order.
+// Used when D is not a multiple of 4 or X is not 16-byte aligned (e.g. the reference's 2-D blobs demo).
+__global__ void segment_sum_generic_kernel(const float* __restrict__ X, const int* __restrict__ order,
+                                           const int* __restrict__ offsets, int K, int D, float* __restrict__ sums) {
+  const int k = blockIdx.x;
+  const int d = blockIdx.y * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float acc = 0.f;
+  for (int p = offsets[k]; p < offsets[k + 1]; ++p) acc += X[(long long)order[p] * D + d];
+  sums[(long long)k * D + d] = acc;
+}
+
 // centers = sums / counts (0/0 -> NaN, as torch's mean over zero rows), per-cluster move norm
 __global__ void finalize_centers_kernel(const float* __restrict__ sums, const float* __restrict__ counts_f, const int* __restrict__ counts_i,
                                         const float* __restrict__ c_old, float* __restrict__ c_new, float* __restrict__ move_norm,

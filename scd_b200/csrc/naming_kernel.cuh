@@ -10,8 +10,12 @@
 // 256 image rows stationary in shared memory (2 x 12 k-blocks x 16 KB, SWIZZLE_128B), streams the
 // vocabulary through a 4-stage TMA ring (SWIZZLE_64B, 32 k per stage), accumulates each
 // 256 x 256 tile in TMEM (2 x 256 columns, double buffered) and the four epilogue warps read the
-// tile back with tcgen05.ld - one thread per image row - keeping a sorted running top-k (and, for
-// the unsupervised driver's softmax, a running max / sum-exp) in registers.  Only [N, k] leaves.
+// tile back with tcgen05.ld - one thread per image row.  The epilogue is a two-level selection: per
+// 32-column chunk only the chunk maximum is computed (31 FMNMX) and compared with the row's k-th best
+// chunk maximum; the rare chunk that beats it is parked (32 floats) in an L2-resident scratch slot.
+// The true top-k of a row lies inside its k chunks with the largest maxima, so one exact scan of
+// those k parked chunks at the end of the vocabulary sweep finishes the row.  (The unsupervised
+// driver's softmax additionally keeps a running max / sum-exp.)  Only [N, k] leaves the SM.
 //
 // Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer (leader CTA only), 2 = TMEM
 // allocator, 3 = idle, 4..7 = epilogue (TMEM lane quadrant = warp & 3).
@@ -53,21 +57,27 @@ static_assert(NameSmem::total <= 232448, "exceeds 227 KB of shared memory");
 struct NameParams {
   long long n_rows;        // N
   long long v_total;       // V (this rank's vocabulary slice length)
-  int n_vsplit;            // vocabulary chunks per row block (work items = row blocks x chunks)
+  // work items: row blocks [0, n_full_rb) sweep the whole vocabulary in one item each; the remaining
+  // (tail-wave) row blocks are split into n_vsplit vocabulary chunks so the last wave fills the GPU
+  int n_full_rb;
+  int n_vsplit;            // vocabulary chunks per tail row block (also the number of partial-result slots)
   int tiles_per_chunk;     // 256-wide tiles per chunk
   int n_row_blocks;        // ceil(N / 256)
   int num_kb;              // ceil(D / 64) live A k-blocks (TMA zero-fills the ragged end of D)
   int want_softmax;
   float scale_log2e;       // scale * log2(e) for the running sum-exp
   // partial results, one slot per vocabulary chunk: [n_vsplit][N][KT] / [n_vsplit][N]
+  // (part_idx is pre-set to -1: slots a row never writes are skipped by the merge)
   float* part_val;
   int* part_idx;
   float* part_max;
   float* part_sum;
+  float* scratch;          // [gridDim.x][128 rows][KT slots][32] parked chunks
 };
 
-// One sorted running top-KT list in registers.  Strict '>' everywhere: among equal scores the
-// lower vocabulary index stays in front (columns are visited in increasing order).
+// One sorted top-KT list in registers, ordered by (value descending, column ascending) - the order
+// torch.topk(..., largest=True, sorted=True) yields when ties resolve to the lower index.  Columns may
+// be pushed in any order.
 template <int KT>
 struct TopK {
   float v[KT];
@@ -76,16 +86,45 @@ struct TopK {
 #pragma unroll
     for (int j = 0; j < KT; ++j) { v[j] = -INFINITY; i[j] = -1; }
   }
-  __device__ __forceinline__ float floor_val() const { return v[KT - 1]; }
+  static __device__ __forceinline__ bool before(float xa, int ia, float xb, int ib) {
+    return xa > xb || (xa == xb && (ib < 0 || ia < ib));
+  }
   __device__ __forceinline__ void push(float x, int col) {
-    if (x > v[KT - 1]) {
+    if (x > -INFINITY && before(x, col, v[KT - 1], i[KT - 1])) {
       v[KT - 1] = x; i[KT - 1] = col;
 #pragma unroll
       for (int j = KT - 1; j > 0; --j) {
-        if (v[j] > v[j - 1]) {
+        if (before(v[j], i[j], v[j - 1], i[j - 1])) {
           float tv = v[j]; v[j] = v[j - 1]; v[j - 1] = tv;
           int ti = i[j]; i[j] = i[j - 1]; i[j - 1] = ti;
         }
+      }
+    }
+  }
+};
+
+// The KT chunks (32 consecutive columns) with the largest chunk maxima seen so far, sorted by maximum
+// (strict '>' on insertion: among equal maxima the earlier chunk stays in front).  slot[] says which
+// scratch slot holds the chunk's 32 values, col[] its first column.
+template <int KT>
+struct ChunkTop {
+  float m[KT];
+  int slot[KT];
+  int col[KT];
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int j = 0; j < KT; ++j) { m[j] = -INFINITY; slot[j] = j; col[j] = -1; }
+  }
+  __device__ __forceinline__ float floor_val() const { return m[KT - 1]; }
+  // the caller has already parked the chunk in slot[KT-1]
+  __device__ __forceinline__ void insert_last(float cmax, int colbase) {
+    m[KT - 1] = cmax; col[KT - 1] = colbase;
+#pragma unroll
+    for (int j = KT - 1; j > 0; --j) {
+      if (m[j] > m[j - 1]) {
+        float tm = m[j]; m[j] = m[j - 1]; m[j - 1] = tm;
+        int ts = slot[j]; slot[j] = slot[j - 1]; slot[j - 1] = ts;
+        int tc = col[j]; col[j] = col[j - 1]; col[j - 1] = tc;
       }
     }
   }
@@ -105,7 +144,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const bool leader = cta_rank == 0;
   const int pair = blockIdx.x >> 1;
   const int n_pairs = gridDim.x >> 1;
-  const int n_items = p.n_row_blocks * p.n_vsplit;
+  const int n_items = p.n_full_rb + (p.n_row_blocks - p.n_full_rb) * p.n_vsplit;
   const int tiles_total = (int)((p.v_total + kTileN - 1) / kTileN);
 
   const int nkb = p.num_kb;
@@ -139,9 +178,11 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + NameSmem::tmem_ptr);
 
   // work item -> (row block, first tile, tile count)
-  auto item_rb = [&](int it) { return it / p.n_vsplit; };
-  auto item_tile0 = [&](int it) { return (it % p.n_vsplit) * p.tiles_per_chunk; };
+  auto item_rb = [&](int it) { return it < p.n_full_rb ? it : p.n_full_rb + (it - p.n_full_rb) / p.n_vsplit; };
+  auto item_chunk = [&](int it) { return it < p.n_full_rb ? 0 : (it - p.n_full_rb) % p.n_vsplit; };
+  auto item_tile0 = [&](int it) { return item_chunk(it) * p.tiles_per_chunk; };
   auto item_ntiles = [&](int it) {
+    if (it < p.n_full_rb) return tiles_total;
     int t0 = item_tile0(it);
     int t1 = min(t0 + p.tiles_per_chunk, tiles_total);
     return max(t1 - t0, 0);
@@ -232,12 +273,45 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const uint32_t quad = warp & 3u;
     const uint32_t lane_addr = (quad * 32u) << 16;
     uint32_t tile_no = 0;
-    TopK<KT> top;
+    ChunkTop<KT> ctop;
+    float4* const my_scratch = reinterpret_cast<float4*>(p.scratch) +
+                               ((size_t)blockIdx.x * kBlockM + quad * 32 + lane) * KT * 8;   // KT slots x 8 float4
     for (int it = pair; it < n_items; it += n_pairs) {
       const int nt = item_ntiles(it);
       const long long row = (long long)item_rb(it) * 2 * kBlockM + cta_rank * kBlockM + quad * 32 + lane;
-      top.reset();
+      ctop.reset();
       float run_max = -INFINITY, run_sum = 0.f;
+
+      // one 32-column chunk of this row: chunk maximum -> filter -> (rarely) park the chunk
+      auto process = [&](uint32_t (&r)[32], int colbase, int n_valid_here) {
+        if (n_valid_here <= 0) return;
+        if (n_valid_here < 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j >= n_valid_here) r[j] = 0xff800000u;   // -inf
+        }
+        float m8[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          m8[g] = fmaxf(fmaxf(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1])),
+                        fmaxf(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])));
+        const float cmax = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+        if (p.want_softmax) {
+          if (cmax > run_max) { run_sum *= exp2f((run_max - cmax) * p.scale_log2e); run_max = cmax; }
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += exp2f((__uint_as_float(r[j]) - run_max) * p.scale_log2e);
+          run_sum += acc;
+        }
+        if (cmax > ctop.floor_val()) {
+          float4* dst = my_scratch + ctop.slot[KT - 1] * 8;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                 __uint_as_float(r[4 * q + 3]));
+          ctop.insert_last(cmax, colbase);
+        }
+      };
+
       for (int t = 0; t < nt; ++t, ++tile_no) {
         const uint32_t buf = tile_no & 1u;
         const int col0 = (item_tile0(it) + t) * kTileN;
@@ -245,39 +319,46 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         ptx::mbar_wait(tmem_full_bar(buf), (tile_no >> 1) & 1u, 600 + buf);
         ptx::tc_fence_after_sync();
         const uint32_t taddr = tmem_base + lane_addr + buf * kTileN;
+        uint32_t ra[32], rb[32];
+        ptx::tmem_ld_32x32(taddr, ra);
 #pragma unroll 1
-        for (int c = 0; c < kTileN / 32; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(taddr + c * 32, r);
-          ptx::tmem_ld_wait();
-          const int cbase = c * 32;
-          if (cbase >= n_valid) continue;
-          if (cbase + 32 > n_valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (cbase + j >= n_valid) r[j] = 0xff800000u;   // -inf
+        for (int c = 0; c < kTileN / 32; c += 2) {
+          ptx::tmem_ld_wait(ra);                                 // ra = chunk c
+          ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);          // in flight while ra is processed
+          process(ra, col0 + c * 32, n_valid - c * 32);
+          ptx::tmem_ld_wait(rb);                                 // rb = chunk c + 1
+          if (c + 2 < kTileN / 32) {
+            ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+          } else {
+            // every column of this accumulator buffer is in registers: hand it back to the MMA issuer
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(tmem_empty_bar(buf) & ptx::kPeerBitMask);
           }
-          float cmax = __uint_as_float(r[0]);
-#pragma unroll
-          for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(r[j]));
-          if (p.want_softmax) {
-            if (cmax > run_max) { run_sum *= exp2f((run_max - cmax) * p.scale_log2e); run_max = cmax; }
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc += exp2f((__uint_as_float(r[j]) - run_max) * p.scale_log2e);
-            run_sum += acc;
-          }
-          if (cmax > top.floor_val()) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) top.push(__uint_as_float(r[j]), col0 + cbase + j);
-          }
+          process(rb, col0 + (c + 1) * 32, n_valid - (c + 1) * 32);
         }
-        // accumulator buffer drained: hand it back to the MMA issuer (leader's barrier)
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(tmem_empty_bar(buf) & ptx::kPeerBitMask);
+      }
+
+      // exact top-k of the row from its (at most KT) parked chunks
+      TopK<KT> top;
+      top.reset();
+#pragma unroll 1
+      for (int e = 0; e < KT; ++e) {
+        // register arrays cannot be indexed dynamically: select entry e with an unrolled scan
+        int slot_e = 0, col_e = -1;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) if (j == e) { slot_e = ctop.slot[j]; col_e = ctop.col[j]; }
+        if (col_e < 0) continue;
+        const float4* src = my_scratch + slot_e * 8;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 x = src[q];
+          top.push(x.x, col_e + 4 * q); top.push(x.y, col_e + 4 * q + 1);
+          top.push(x.z, col_e + 4 * q + 2); top.push(x.w, col_e + 4 * q + 3);
+        }
       }
       if (row < p.n_rows) {
-        const long long slot = (long long)(it % p.n_vsplit) * p.n_rows + row;
+        const long long slot = (long long)item_chunk(it) * p.n_rows + row;
 #pragma unroll
         for (int j = 0; j < KT; ++j) { p.part_val[slot * KT + j] = top.v[j]; p.part_idx[slot * KT + j] = top.i[j]; }
         p.part_max[slot] = run_max;
@@ -310,6 +391,7 @@ __global__ void topk_merge_kernel(const float* __restrict__ part_val, const IdxT
   float M = -INFINITY;
   for (int q = 0; q < parts; ++q) {
     const long long slot = (long long)q * n_rows + row;
+    if ((long long)part_idx[slot * kt_in] < 0) continue;       // this row has nothing in part q
     for (int j = 0; j < kt_in; ++j) {
       const float x = part_val[slot * kt_in + j];
       const long long id = (long long)part_idx[slot * kt_in + j];
@@ -329,6 +411,7 @@ __global__ void topk_merge_kernel(const float* __restrict__ part_val, const IdxT
   if (part_max) {
     for (int q = 0; q < parts; ++q) {
       const long long slot = (long long)q * n_rows + row;
+      if ((long long)part_idx[slot * kt_in] < 0) continue;
       const float m = part_max[slot];
       if (m > -INFINITY) S += part_sum[slot] * expf(scale * (m - M));
     }

@@ -97,10 +97,11 @@ struct NamePlan {
   int kt;                 // compiled list length (1, 5 or 8)
   int n_row_blocks;
   int tiles_total;
-  int n_vsplit;
+  int n_full_rb;          // row blocks that sweep the whole vocabulary as one work item
+  int n_vsplit;           // vocabulary chunks of the remaining (tail-wave) row blocks
   int tiles_per_chunk;
   int n_pairs;
-  size_t off_val, off_idx, off_max, off_sum, bytes;
+  size_t off_val, off_idx, off_max, off_sum, off_scratch, idx_bytes, bytes;
 };
 
 bool plan_naming(int64_t N, int64_t V, int k, NamePlan* pl) {
@@ -109,30 +110,33 @@ bool plan_naming(int64_t N, int64_t V, int k, NamePlan* pl) {
   pl->n_row_blocks = (int)((N + 2 * scd::kBlockM - 1) / (2 * scd::kBlockM));
   pl->tiles_total = (int)((V + scd::kTileN - 1) / scd::kTileN);
   const int pairs_hw = std::max(1, device_sm_count() / 2);
-  // pick the vocabulary split that fills the CTA pairs best (items = row blocks x chunks)
+  // Whole waves of row blocks keep the vocabulary sweep in one piece (the running top-k threshold stays
+  // warm, which is what makes the epilogue cheap); only the last, partial wave is split along the
+  // vocabulary so that it still fills every CTA pair.
+  pl->n_full_rb = (pl->n_row_blocks / pairs_hw) * pairs_hw;
+  const int tail_rb = pl->n_row_blocks - pl->n_full_rb;
   int best_s = 1;
-  double best_eff = -1.0;
+  double best_cost = 1e30;
   const int max_s = std::max(1, std::min(pl->tiles_total, 16));
-  for (int s = 1; s <= max_s; ++s) {
+  for (int s = 1; s <= max_s && tail_rb > 0; ++s) {
     const int tpc = (pl->tiles_total + s - 1) / s;
-    const int s_eff = (pl->tiles_total + tpc - 1) / tpc;
-    if (s_eff != s) continue;
-    const long long items = (long long)pl->n_row_blocks * s;
+    if ((pl->tiles_total + tpc - 1) / tpc != s) continue;            // every chunk must be non-empty
+    const long long items = (long long)tail_rb * s;
     const long long waves = (items + pairs_hw - 1) / pairs_hw;
-    // useful tile-steps over issued tile-steps, with a small charge per extra A reload
-    const double eff = (double)pl->n_row_blocks * pl->tiles_total / ((double)waves * pairs_hw * tpc) - 0.004 * (s - 1);
-    if (eff > best_eff + 1e-9) { best_eff = eff; best_s = s; }
+    const double cost = (double)waves * tpc / pl->tiles_total + 0.01 * (s - 1);   // tail time in full sweeps
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s; }
   }
   pl->n_vsplit = std::max(1, best_s);
   pl->tiles_per_chunk = std::max(1, (pl->tiles_total + pl->n_vsplit - 1) / pl->n_vsplit);
-  const long long items = (long long)pl->n_row_blocks * pl->n_vsplit;
+  const long long items = pl->n_full_rb + (long long)tail_rb * pl->n_vsplit;
   pl->n_pairs = (int)std::max<long long>(1, std::min<long long>(pairs_hw, items));
   size_t o = 0;
   const size_t slots = (size_t)pl->n_vsplit * (size_t)N;
   pl->off_val = o; o = align_up(o + slots * pl->kt * sizeof(float), 256);
-  pl->off_idx = o; o = align_up(o + slots * pl->kt * sizeof(int), 256);
+  pl->off_idx = o; pl->idx_bytes = slots * pl->kt * sizeof(int); o = align_up(o + pl->idx_bytes, 256);
   pl->off_max = o; o = align_up(o + slots * sizeof(float), 256);
   pl->off_sum = o; o = align_up(o + slots * sizeof(float), 256);
+  pl->off_scratch = o; o = align_up(o + (size_t)2 * pairs_hw * scd::kBlockM * pl->kt * 32 * sizeof(float), 256);
   pl->bytes = std::max<size_t>(o, 256);
   return true;
 }
@@ -220,22 +224,25 @@ int scd_mstep_sums(const float* X, const int64_t* labels, int64_t N, int D, int 
                    size_t ws_bytes, scd_stream_t stream) {
   if (N < 0 || D <= 0 || K <= 0) return fail("scd_mstep_sums: bad shape N=%lld D=%d K=%d", (long long)N, D, K);
   if (N >= (1ll << 31)) return fail("scd_mstep_sums: N=%lld exceeds the int32 row-index range", (long long)N);
-  if (D % 4 != 0 || D > 128 * scd::kSegMaxVec + 124) return fail("scd_mstep_sums: D=%d must be a multiple of 4 and <= %d", D, 128 * scd::kSegMaxVec + 124);
+  const bool vec_ok = D % 4 == 0 && D <= 128 * scd::kSegMaxVec + 124 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
   if (K * sizeof(int) > 48 * 1024) return fail("scd_mstep_sums: K=%d too large for the shared-memory histogram", K);
   if (!sums || !counts || !ws) return fail("scd_mstep_sums: null pointer");
   if (ws_bytes < scd_mstep_workspace_bytes(N, K)) return fail("scd_mstep_sums: workspace too small (%zu < %zu)", ws_bytes, scd_mstep_workspace_bytes(N, K));
-  if ((reinterpret_cast<uintptr_t>(X) & 15) != 0) return fail("scd_mstep_sums: X must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   int* offsets = reinterpret_cast<int*>(ws);
   int* cursor = offsets + K + 1;
   int* order = cursor + K;
   SCD_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * (size_t)K * D, st));
   if (int e = sort_rows_by_label(labels, N, K, counts, offsets, cursor, order, st)) return e;
-  if (N > 0) {
+  if (N > 0 && vec_ok) {
     const long long warps = (N + scd::kSegRows - 1) / scd::kSegRows;
     const long long blocks = (warps * 32 + 255) / 256;
     scd::segment_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, order, offsets, K, D, sums);
     SCD_LAUNCH_CHECK("segment_sum_kernel");
+  } else if (N > 0) {
+    dim3 grid((unsigned)K, (unsigned)((D + 127) / 128));
+    scd::segment_sum_generic_kernel<<<grid, 128, 0, st>>>(X, order, offsets, K, D, sums);
+    SCD_LAUNCH_CHECK("segment_sum_generic_kernel");
   }
   return 0;
 }
@@ -323,6 +330,7 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
   scd::NameParams p;
   p.n_rows = N;
   p.v_total = V;
+  p.n_full_rb = pl.n_full_rb;
   p.n_vsplit = pl.n_vsplit;
   p.tiles_per_chunk = pl.tiles_per_chunk;
   p.n_row_blocks = pl.n_row_blocks;
@@ -333,6 +341,8 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
   p.part_idx = reinterpret_cast<int*>(w8 + pl.off_idx);
   p.part_max = reinterpret_cast<float*>(w8 + pl.off_max);
   p.part_sum = reinterpret_cast<float*>(w8 + pl.off_sum);
+  p.scratch = reinterpret_cast<float*>(w8 + pl.off_scratch);
+  if (pl.n_vsplit > 1) SCD_CUDA(cudaMemsetAsync(p.part_idx, 0xFF, pl.idx_bytes, st));   // -1: "row has nothing in this part"
 
   int e = 0;
   if (pl.kt == 1) e = launch_name_topk<1>(mx, mw, p, pl.n_pairs, st);
