@@ -335,7 +335,7 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
   p.tiles_per_chunk = pl.tiles_per_chunk;
   p.n_row_blocks = pl.n_row_blocks;
   p.num_kb = (D + scd::kAKBlock - 1) / scd::kAKBlock;
-  p.want_softmax = want_softmax ? 1 : 0;
+  p.want_softmax = (want_softmax || row_max || row_sumexp) ? 1 : 0;     // running max / sum-exp needed
   p.scale_log2e = scale * 1.4426950408889634f;
   p.part_val = reinterpret_cast<float*>(w8 + pl.off_val);
   p.part_idx = reinterpret_cast<int*>(w8 + pl.off_idx);
@@ -350,7 +350,7 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
   else e = launch_name_topk<8>(mx, mw, p, pl.n_pairs, st);
   if (e) return e;
 
-  const bool stats = want_softmax || row_max;
+  const bool stats = want_softmax || row_max || row_sumexp;
   scd::topk_merge_kernel<int, false><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(
       p.part_val, p.part_idx, stats ? p.part_max : nullptr, stats ? p.part_sum : nullptr, pl.n_vsplit, N, pl.kt, k, scale,
       want_softmax ? 1 : 0, idx_offset, vals, reinterpret_cast<long long*>(idx), row_max, row_sumexp);
