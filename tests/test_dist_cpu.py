@@ -1,0 +1,65 @@
+"""CPU-only, world_size 2 over gloo: the host-side logic of the sharded path - shard bounds, the packed
+[K*D sums | K counts | inertia] all-reduce of the k-means M-step, and the all-gather plumbing of the
+vocabulary-sharded top-k (the merge itself is a CUDA kernel, covered by the GPU tests)."""
+import os
+import socket
+import types
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from scd_b200 import dist as sdist
+
+
+def test_shard_bounds_cover_everything_once():
+    for total in (0, 1, 7, 100, 127000, 21000):
+        for world in (1, 2, 3, 8):
+            cuts = [sdist.shard_bounds(total, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == total
+            for (a, b), (c, d) in zip(cuts, cuts[1:]):
+                assert b == c and a <= b and c <= d
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, k, d):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from scd_b200 import kmeans
+        g = torch.Generator().manual_seed(0)
+        n = 101
+        X = torch.randn(n, d, generator=g)
+        labels = torch.randint(0, k, (n,), generator=g)
+        lo, hi = sdist.shard_bounds(n, world, rank)
+        # what the M-step kernel would have produced on this rank's row shard
+        ms = types.SimpleNamespace(k=k, d=d, sums=torch.zeros(k, d), counts=torch.zeros(k, dtype=torch.int32))
+        ms.sums.index_add_(0, labels[lo:hi], X[lo:hi])
+        ms.counts += torch.bincount(labels[lo:hi], minlength=k).int()
+        inertia = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        km = kmeans.K_Means(k=k, process_group=dist.group.WORLD)
+        counts_f = km._allreduce(ms, inertia)
+        want = torch.zeros(k, d).index_add_(0, labels, X)
+        assert torch.allclose(ms.sums, want, atol=1e-5)
+        assert torch.equal(counts_f.long(), torch.bincount(labels, minlength=k))
+        assert inertia.item() == sum(range(1, world + 1))
+        # all-gather plumbing used by sharded_score_topk: every rank ends with every shard's list, in rank order
+        mine = torch.full((4, 5), float(rank))
+        got = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(got, mine)
+        assert [float(t[0, 0]) for t in got] == [float(r) for r in range(world)]
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_packed_allreduce_world2_gloo():
+    mp.spawn(_worker, args=(2, _free_port(), 6, 16), nprocs=2, join=True)
