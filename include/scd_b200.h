@@ -45,9 +45,15 @@ SCD_API int scd_pairwise_distance(const float* X, int64_t N, int D, const float*
                           float* out /* nullable */, int32_t* cost_x1000 /* nullable */, scd_stream_t stream);
 
 /* E-step, faster_mix_k_means_pytorch.py:58-60 / :105-107: labels = argmin_k dist (ties -> lowest k, NaN wins),
- * mindist = min_k dist, *inertia_acc += sum(mindist) (fp64 accumulator, caller zeroes it). */
+ * mindist = min_k dist, *inertia_acc += sum(mindist) (fp64 accumulator, caller zeroes it).
+ * Tensor-core path (D % 4 == 0, K <= 1024, X 16-byte aligned): ||x||^2 - 2 x.c + ||c||^2 with the contraction
+ * issued as three bf16 tcgen05 MMAs (hi/lo split of x and c, fp32 accumulate; X is read once, as fp32).
+ * Other shapes: the fp32 direct-form kernel of scd_pairwise_distance with the argmin fused (exact = 1 forces it).
+ * ws holds the per-iteration centroid hi/lo planes and norms. */
+SCD_API size_t scd_estep_workspace_bytes(int K, int D);
 SCD_API int scd_estep(const float* X, int64_t N, int D, const float* C, int K,
-              int64_t* labels, float* mindist /* nullable */, double* inertia_acc /* nullable */, scd_stream_t stream);
+              int64_t* labels, float* mindist /* nullable */, double* inertia_acc /* nullable */, int exact,
+              void* ws, size_t ws_bytes, scd_stream_t stream);
 
 /* Labelled-row inertia, faster_mix_k_means_pytorch.py:108-109: *acc += sum_i ||L[i]-C[labels[i]]||^2. */
 SCD_API int scd_labelled_inertia(const float* L, const int64_t* labels, int64_t n, int D, const float* C, int K,

@@ -18,7 +18,8 @@ SIGNATURES = {
     'scd_version': (_int, []),
     'scd_last_error': (C.c_char_p, []),
     'scd_pairwise_distance': (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp]),
-    'scd_estep': (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _vp]),
+    'scd_estep_workspace_bytes': (_sz, [_int, _int]),
+    'scd_estep': (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
     'scd_labelled_inertia': (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp, _vp]),
     'scd_mstep_workspace_bytes': (_sz, [_i64, _int]),
     'scd_mstep_sums': (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _sz, _vp]),

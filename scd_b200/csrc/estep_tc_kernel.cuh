@@ -1,0 +1,307 @@
+// k-means E-step on the tcgen05 tensor cores (SURVEY 8a rows a1 + a2).
+//
+//   dist[n, k] = ||x_n||^2 - 2 x_n . c_k + ||c_k||^2      labels[n] = argmin_k (ties -> lowest k, NaN wins)
+//   replaces  pairwise_distance (local_utils/faster_mix_k_means_pytorch.py:177-212) + torch.min (:59 / :106)
+//
+// The reference computes sum_d (x - c)^2 directly in fp32.  A single bf16 pass of the x.c contraction
+// cannot keep its 1e-4 / argmin-margin parity once the centroids are fp32 means,
+// so the contraction is issued as three bf16 MMAs with fp32 accumulation:
+//     x.c ~= x_hi.c_hi + x_hi.c_lo + x_lo.c_hi        (x_hi = bf16(x), x_lo = bf16(x - x_hi); same for c)
+// which measures 3.8e-7 max abs error on unit-norm data (the fp32 direct form: 2.6e-7).
+//
+// X stays fp32 in HBM and is read exactly ONCE per E-step: TMA brings 128 x 32 fp32 tiles into a ring,
+// four converter warps (thread = row) split them into the hi / lo bf16 K-major operand tiles in shared
+// memory (SWIZZLE_64B layout written by hand, fence.proxy.async, mbarrier hand-off to the MMA warp) and
+// accumulate ||x||^2 on the way.  The centroid hi / lo planes (+ ||c||^2) are prepared per iteration by a
+// tiny kernel and streamed from L2.  Accumulators live in TMEM (2 x 256 columns, double buffered); the
+// epilogue warps (thread = row) fold  ||c||^2 - 2 acc  into a running argmin, so [N, K] never exists.
+// HBM-bound while 3 * K <~ 500 (K = 100 / 120 / 200); tensor-bound for K = 1000.
+//
+// Warp roles (384 threads, 1 CTA / SM, persistent over 128-row tiles):
+//   0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle | 4-7 converters | 8-11 epilogue
+#pragma once
+#include "ptx.cuh"
+#include <cuda_bf16.h>
+
+namespace scd {
+
+constexpr int kEsBM = 128;              // rows per tile
+constexpr int kEsBK = 32;               // k per stage
+constexpr int kEsXStages = 4;           // fp32 X ring
+constexpr int kEsAStages = 3;           // converted hi/lo ring
+constexpr int kEsBStages = 3;           // centroid hi/lo ring
+constexpr int kEsXBytes = kEsBM * kEsBK * 4;          // 16384
+constexpr int kEsAPlane = kEsBM * kEsBK * 2;          // 8192 (one of hi / lo)
+constexpr int kEsBPlane = 256 * kEsBK * 2;            // 16384 (capacity for N = 256)
+constexpr int kEsThreads = 384;
+constexpr int kEsMaxK = 1024;
+
+struct EsSmem {
+  static constexpr int x_off = 0;
+  static constexpr int a_off = x_off + kEsXStages * kEsXBytes;                  // 65536
+  static constexpr int b_off = a_off + kEsAStages * 2 * kEsAPlane;              // 114688
+  static constexpr int bar_off = b_off + kEsBStages * 2 * kEsBPlane;            // 212992
+  static constexpr int x_full = bar_off;                                        // [4]
+  static constexpr int x_empty = x_full + 8 * kEsXStages;
+  static constexpr int a_full = x_empty + 8 * kEsXStages;                       // [3]
+  static constexpr int a_empty = a_full + 8 * kEsAStages;
+  static constexpr int b_full = a_empty + 8 * kEsAStages;                       // [3]
+  static constexpr int b_empty = b_full + 8 * kEsBStages;
+  static constexpr int t_full = b_empty + 8 * kEsBStages;                       // [2]
+  static constexpr int t_empty = t_full + 16;
+  static constexpr int tmem_ptr = t_empty + 16;
+  static constexpr int cnorm = tmem_ptr + 16;                                   // [kEsMaxK] floats
+  static constexpr int xnorm = cnorm + 4 * kEsMaxK;                             // [4][128] floats
+  static constexpr int total = xnorm + 4 * 4 * kEsBM;
+};
+static_assert(EsSmem::total + 1024 <= 232448, "exceeds 227 KB of shared memory");
+
+struct EsParams {
+  long long n_rows;
+  int n_clusters;          // K
+  int n_tile;              // UMMA N (multiple of 16, <= 256)
+  int n_ntiles;            // ceil(K / 256) (1 for K <= 256)
+  int num_kb;              // ceil(D / 32)
+  int n_row_tiles;
+  const float* cnorm;      // [K]
+  long long* labels;       // [N]
+  float* mindist;          // nullable [N]
+  double* inertia;         // nullable
+};
+
+// fp32 centroids -> bf16 hi / lo planes [K, D] + ||c||^2
+__global__ void centroid_split_kernel(const float* __restrict__ C, int K, int D, __nv_bfloat16* __restrict__ hi,
+                                      __nv_bfloat16* __restrict__ lo, float* __restrict__ cnorm) {
+  const int k = blockIdx.x;
+  float part = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float c = C[(long long)k * D + d];
+    const __nv_bfloat16 h = __float2bfloat16_rn(c);
+    hi[(long long)k * D + d] = h;
+    lo[(long long)k * D + d] = __float2bfloat16_rn(c - __bfloat162float(h));
+    part = fmaf(c, c, part);
+  }
+  __shared__ float sh[32];
+  for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)((blockDim.x + 31) / 32); ++w) t += sh[w];
+    cnorm[k] = t;
+  }
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ bool es_better(float cand, float cur) {
+  return (cand < cur) || (cand != cand && cur == cur);      // torch.min: strict '<', a NaN beats any number
+}
+
+__global__ void __launch_bounds__(kEsThreads, 1)
+estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_chi,
+                const __grid_constant__ CUtensorMap map_clo, const EsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = ptx::smem_u32(smem);
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const int nkb = p.num_kb;
+
+  auto bar = [&](int base, int i) { return sbase + base + 8 * i; };
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_x);
+    ptx::prefetch_tensormap(&map_chi);
+    ptx::prefetch_tensormap(&map_clo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kEsXStages; ++s) { ptx::mbar_init(bar(EsSmem::x_full, s), 1); ptx::mbar_init(bar(EsSmem::x_empty, s), 4); }
+    for (int s = 0; s < kEsAStages; ++s) { ptx::mbar_init(bar(EsSmem::a_full, s), 4); ptx::mbar_init(bar(EsSmem::a_empty, s), 1); }
+    for (int s = 0; s < kEsBStages; ++s) { ptx::mbar_init(bar(EsSmem::b_full, s), 1); ptx::mbar_init(bar(EsSmem::b_empty, s), 1); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(bar(EsSmem::t_full, b), 1); ptx::mbar_init(bar(EsSmem::t_empty, b), 4); }
+    ptx::fence_mbar_init_cluster();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<1>(sbase + EsSmem::tmem_ptr, 512);
+    ptx::tmem_relinquish<1>();
+  }
+  {
+    float* cn = reinterpret_cast<float*>(smem + EsSmem::cnorm);
+    for (int k = threadIdx.x; k < p.n_clusters; k += blockDim.x) cn[k] = p.cnorm[k];
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + EsSmem::tmem_ptr);
+
+  if (warp == 0) {
+    // =================================================== TMA producer
+    if (lane == 0) {
+      int xs = 0, bs = 0; uint32_t xph = 0, bph = 0;
+      const uint32_t b_bytes = 2u * (uint32_t)p.n_tile * kEsBK * 2u;
+      for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x) {
+        for (int nt = 0; nt < p.n_ntiles; ++nt) {
+          for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_wait(bar(EsSmem::x_empty, xs), xph ^ 1, 700 + xs);
+            ptx::mbar_arrive_expect_tx(bar(EsSmem::x_full, xs), kEsXBytes);
+            ptx::tma_load_2d<1>(sbase + EsSmem::x_off + xs * kEsXBytes, &map_x, bar(EsSmem::x_full, xs), kb * kEsBK, rt * kEsBM,
+                                p.n_ntiles > 1 ? ptx::kEvictNormal : ptx::kEvictFirst);
+            if (++xs == kEsXStages) { xs = 0; xph ^= 1; }
+            ptx::mbar_wait(bar(EsSmem::b_empty, bs), bph ^ 1, 710 + bs);
+            ptx::mbar_arrive_expect_tx(bar(EsSmem::b_full, bs), b_bytes);
+            const uint32_t bdst = sbase + EsSmem::b_off + bs * 2 * kEsBPlane;
+            ptx::tma_load_2d<1>(bdst, &map_chi, bar(EsSmem::b_full, bs), kb * kEsBK, nt * 256, ptx::kEvictLast);
+            ptx::tma_load_2d<1>(bdst + kEsBPlane, &map_clo, bar(EsSmem::b_full, bs), kb * kEsBK, nt * 256, ptx::kEvictLast);
+            if (++bs == kEsBStages) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16_f32(kEsBM, (uint32_t)p.n_tile);
+      int as = 0, bs = 0; uint32_t aph = 0, bph = 0, tile_no = 0;
+      for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x) {
+        for (int nt = 0; nt < p.n_ntiles; ++nt, ++tile_no) {
+          const uint32_t buf = tile_no & 1u;
+          ptx::mbar_wait(bar(EsSmem::t_empty, buf), ((tile_no >> 1) & 1u) ^ 1u, 720 + buf);
+          ptx::tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + buf * 256;
+          for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_wait(bar(EsSmem::a_full, as), aph, 730 + as);
+            ptx::mbar_wait(bar(EsSmem::b_full, bs), bph, 740 + bs);
+            ptx::tc_fence_after_sync();
+            const uint32_t a_hi = sbase + EsSmem::a_off + as * 2 * kEsAPlane, a_lo = a_hi + kEsAPlane;
+            const uint32_t b_hi = sbase + EsSmem::b_off + bs * 2 * kEsBPlane, b_lo = b_hi + kEsBPlane;
+#pragma unroll
+            for (int kk = 0; kk < kEsBK / 16; ++kk) {
+              const uint32_t ko = kk * 32;          // 16 bf16 = 32 bytes inside the 64-byte swizzle atom
+              const uint64_t dah = ptx::make_kmajor_desc(a_hi + ko, 64), dal = ptx::make_kmajor_desc(a_lo + ko, 64);
+              const uint64_t dbh = ptx::make_kmajor_desc(b_hi + ko, 64), dbl = ptx::make_kmajor_desc(b_lo + ko, 64);
+              ptx::umma_bf16<1>(d_tmem, dah, dbh, idesc, (kb | kk) != 0 ? 1u : 0u);
+              ptx::umma_bf16<1>(d_tmem, dah, dbl, idesc, 1u);
+              ptx::umma_bf16<1>(d_tmem, dal, dbh, idesc, 1u);
+            }
+            ptx::umma_commit<1>(bar(EsSmem::a_empty, as), 0);
+            ptx::umma_commit<1>(bar(EsSmem::b_empty, bs), 0);
+            if (++as == kEsAStages) { as = 0; aph ^= 1; }
+            if (++bs == kEsBStages) { bs = 0; bph ^= 1; }
+          }
+          ptx::umma_commit<1>(bar(EsSmem::t_full, buf), 0);
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // =================================================== converters: fp32 tile -> bf16 hi / lo operand tiles
+    const int row = (int)(warp - 4) * 32 + (int)lane;
+    const uint32_t x_row = (uint32_t)row * 128u, x_sw = (uint32_t)(row & 7);
+    const uint32_t a_row = (uint32_t)row * 64u, a_sw = (uint32_t)((row >> 1) & 3);
+    float* xnorm_s = reinterpret_cast<float*>(smem + EsSmem::xnorm);
+    int xs = 0, as = 0; uint32_t xph = 0, aph = 0;
+    for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x) {
+      for (int nt = 0; nt < p.n_ntiles; ++nt) {
+        float norm = 0.f;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(bar(EsSmem::x_full, xs), xph, 750 + xs);
+          const uint8_t* xt = smem + EsSmem::x_off + xs * kEsXBytes + x_row;
+          float4 f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = *reinterpret_cast<const float4*>(xt + ((((uint32_t)j) ^ x_sw) << 4));
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar(EsSmem::x_empty, xs));      // the fp32 stage is in registers
+          if (++xs == kEsXStages) { xs = 0; xph ^= 1; }
+          uint4 hi[4], lo[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float v[8] = {f[2 * c].x, f[2 * c].y, f[2 * c].z, f[2 * c].w, f[2 * c + 1].x, f[2 * c + 1].y, f[2 * c + 1].z, f[2 * c + 1].w};
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+              const float r0 = v[2 * q] - __bfloat162float(hh.x), r1 = v[2 * q + 1] - __bfloat162float(hh.y);
+              const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
+              h[q] = *reinterpret_cast<const uint32_t*>(&hh);
+              l[q] = *reinterpret_cast<const uint32_t*>(&ll);
+              norm = fmaf(v[2 * q], v[2 * q], norm);
+              norm = fmaf(v[2 * q + 1], v[2 * q + 1], norm);
+            }
+            hi[c] = make_uint4(h[0], h[1], h[2], h[3]);
+            lo[c] = make_uint4(l[0], l[1], l[2], l[3]);
+          }
+          ptx::mbar_wait(bar(EsSmem::a_empty, as), aph ^ 1, 760 + as);
+          uint8_t* at = smem + EsSmem::a_off + as * 2 * kEsAPlane + a_row;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t off = (((uint32_t)c) ^ a_sw) << 4;
+            *reinterpret_cast<uint4*>(at + off) = hi[c];
+            *reinterpret_cast<uint4*>(at + kEsAPlane + off) = lo[c];
+          }
+          if (kb == nkb - 1 && nt == 0) xnorm_s[(rt & 3) * kEsBM + row] = norm;
+          fence_proxy_async_smem();                                       // generic-proxy writes -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar(EsSmem::a_full, as));
+          if (++as == kEsAStages) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // =================================================== epilogue: running argmin per row
+    const uint32_t quad = warp & 3u;
+    const int row_in_tile = (int)quad * 32 + (int)lane;
+    const uint32_t lane_addr = (quad * 32u) << 16;
+    const float* cn = reinterpret_cast<const float*>(smem + EsSmem::cnorm);
+    const float* xnorm_s = reinterpret_cast<const float*>(smem + EsSmem::xnorm);
+    uint32_t tile_no = 0;
+    double inertia_local = 0.0;
+    for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x) {
+      float best = INFINITY; int best_k = -1;
+      float xn = 0.f;
+      for (int nt = 0; nt < p.n_ntiles; ++nt, ++tile_no) {
+        const uint32_t buf = tile_no & 1u;
+        ptx::mbar_wait(bar(EsSmem::t_full, buf), (tile_no >> 1) & 1u, 770 + buf);
+        ptx::tc_fence_after_sync();
+        if (nt == 0) xn = xnorm_s[(rt & 3) * kEsBM + row_in_tile];
+        const uint32_t taddr = tmem_base + lane_addr + buf * 256;
+        const int k0 = nt * 256;
+        const int n_here = min(p.n_clusters - k0, 256);
+#pragma unroll 1
+        for (int c = 0; c * 32 < p.n_tile; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, r);     // columns past n_tile are stale TMEM, masked below
+          ptx::tmem_ld_wait(r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int kk = c * 32 + j;
+            if (kk < n_here) {
+              const float d = fmaf(-2.f, __uint_as_float(r[j]), cn[k0 + kk]);
+              if (best_k < 0 || es_better(d, best)) { best = d; best_k = k0 + kk; }
+            }
+          }
+        }
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar(EsSmem::t_empty, buf));
+      }
+      const long long row = (long long)rt * kEsBM + row_in_tile;
+      if (row < p.n_rows) {
+        float d = xn + best;
+        d = d < 0.f ? 0.f : d;                    // the direct form is never negative; keeps NaN
+        p.labels[row] = best_k;
+        if (p.mindist) p.mindist[row] = d;
+        inertia_local += (double)d;
+      }
+    }
+    if (p.inertia) {
+      for (int off = 16; off > 0; off >>= 1) inertia_local += __shfl_down_sync(0xffffffffu, inertia_local, off);
+      if (lane == 0) atomicAdd(p.inertia, inertia_local);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<1>(tmem_base, 512);
+}
+
+}  // namespace scd

@@ -14,6 +14,7 @@
 #include <mutex>
 #include <string>
 
+#include "estep_tc_kernel.cuh"
 #include "kmeans_kernel.cuh"
 #include "naming_kernel.cuh"
 #include "vote_kernel.cuh"
@@ -76,16 +77,17 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, box_cols], inner (cols) swizzled
-int make_map_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
-                  CUtensorMapSwizzle swz) {
+// 2-D row-major [rows, cols] tensor (bf16 or fp32), box = [box_rows, box_cols], inner (cols) swizzled
+int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
+                CUtensorMapSwizzle swz, bool is_f32 = false) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
+  cuuint64_t strides[1] = {cols * (is_f32 ? 4u : 2u)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                  dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)", (int)r,
                                      (unsigned long long)rows, (unsigned long long)cols);
@@ -174,15 +176,58 @@ int scd_pairwise_distance(const float* X, int64_t N, int D, const float* C, int 
   return 0;
 }
 
+size_t scd_estep_workspace_bytes(int K, int D) {
+  if (K <= 0 || D <= 0) return 256;
+  return align_up((size_t)K * D * 2, 256) * 2 + align_up((size_t)K * sizeof(float), 256) + 256;
+}
+
 int scd_estep(const float* X, int64_t N, int D, const float* C, int K, int64_t* labels, float* mindist, double* inertia_acc,
-              scd_stream_t stream) {
+              int exact, void* ws, size_t ws_bytes, scd_stream_t stream) {
   if (N < 0 || D <= 0 || K <= 0) return fail("scd_estep: bad shape N=%lld D=%d K=%d", (long long)N, D, K);
   if (N == 0) return 0;
   if (!X || !C || !labels) return fail("scd_estep: null pointer");
-  dim3 grid((unsigned)((N + scd::kDistBM - 1) / scd::kDistBM));
-  scd::sqdist_kernel<true><<<grid, scd::kDistThreads, 0, as_stream(stream)>>>(X, N, D, C, K, nullptr, nullptr,
-                                                                              reinterpret_cast<long long*>(labels), mindist, inertia_acc);
-  SCD_LAUNCH_CHECK("sqdist_kernel<fused argmin>");
+  cudaStream_t st = as_stream(stream);
+  const bool tc_ok = !exact && D % 4 == 0 && K <= scd::kEsMaxK && N < (1ll << 31) &&
+                     (reinterpret_cast<uintptr_t>(X) & 15) == 0 && ws && ws_bytes >= scd_estep_workspace_bytes(K, D);
+  if (!tc_ok) {
+    dim3 grid((unsigned)((N + scd::kDistBM - 1) / scd::kDistBM));
+    scd::sqdist_kernel<true><<<grid, scd::kDistThreads, 0, st>>>(X, N, D, C, K, nullptr, nullptr,
+                                                                 reinterpret_cast<long long*>(labels), mindist, inertia_acc);
+    SCD_LAUNCH_CHECK("sqdist_kernel<fused argmin>");
+    return 0;
+  }
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  const size_t plane = align_up((size_t)K * D * 2, 256);
+  __nv_bfloat16* chi = reinterpret_cast<__nv_bfloat16*>(w8);
+  __nv_bfloat16* clo = reinterpret_cast<__nv_bfloat16*>(w8 + plane);
+  float* cnorm = reinterpret_cast<float*>(w8 + 2 * plane);
+  scd::centroid_split_kernel<<<K, 256, 0, st>>>(C, K, D, chi, clo, cnorm);
+  SCD_LAUNCH_CHECK("centroid_split_kernel");
+
+  scd::EsParams p;
+  p.n_rows = N;
+  p.n_clusters = K;
+  p.n_ntiles = (K + 255) / 256;
+  p.n_tile = p.n_ntiles > 1 ? 256 : ((K + 15) / 16) * 16;
+  p.num_kb = (D + scd::kEsBK - 1) / scd::kEsBK;
+  p.n_row_tiles = (int)((N + scd::kEsBM - 1) / scd::kEsBM);
+  p.cnorm = cnorm;
+  p.labels = reinterpret_cast<long long*>(labels);
+  p.mindist = mindist;
+  p.inertia = inertia_acc;
+  CUtensorMap mx, mhi, mlo;
+  if (int e = make_map_2d(&mx, X, (uint64_t)N, (uint64_t)D, scd::kEsBM, scd::kEsBK, CU_TENSOR_MAP_SWIZZLE_128B, true)) return e;
+  if (int e = make_map_2d(&mhi, chi, (uint64_t)K, (uint64_t)D, (uint32_t)p.n_tile, scd::kEsBK, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+  if (int e = make_map_2d(&mlo, clo, (uint64_t)K, (uint64_t)D, (uint32_t)p.n_tile, scd::kEsBK, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+  static bool attr_set = false;
+  const int smem = scd::EsSmem::total + 1024;
+  if (!attr_set) {
+    SCD_CUDA(cudaFuncSetAttribute(scd::estep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int grid = std::min(device_sm_count(), p.n_row_tiles);
+  scd::estep_tc_kernel<<<grid, scd::kEsThreads, smem, st>>>(mx, mhi, mlo, p);
+  SCD_LAUNCH_CHECK("estep_tc_kernel");
   return 0;
 }
 
@@ -323,8 +368,8 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
   cudaStream_t st = as_stream(stream);
 
   CUtensorMap mx, mw;
-  if (int e = make_map_bf16(&mx, X, (uint64_t)N, (uint64_t)D, scd::kBlockM, scd::kAKBlock, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  if (int e = make_map_bf16(&mw, Wt, (uint64_t)V, (uint64_t)D, scd::kTileN / 2, scd::kBK, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+  if (int e = make_map_2d(&mx, X, (uint64_t)N, (uint64_t)D, scd::kBlockM, scd::kAKBlock, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  if (int e = make_map_2d(&mw, Wt, (uint64_t)V, (uint64_t)D, scd::kTileN / 2, scd::kBK, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
 
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
   scd::NameParams p;

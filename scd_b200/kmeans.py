@@ -36,10 +36,18 @@ def _dev_f32(t: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- thin kernel wrappers
-def _estep(X, C, labels_out, inertia_acc, mindist=None):
+_ESTEP_WS = {}
+
+
+def _estep(X, C, labels_out, inertia_acc, mindist=None, exact=False):
     lib = _lib.load()
+    key = (int(C.shape[0]), int(C.shape[1]), X.device.index)
+    ws = _ESTEP_WS.get(key)
+    if ws is None:
+        ws = _ESTEP_WS[key] = torch.empty(lib.scd_estep_workspace_bytes(key[0], key[1]), dtype=torch.uint8, device=X.device)
     _lib.check(lib.scd_estep(X.data_ptr(), X.shape[0], X.shape[1], C.data_ptr(), C.shape[0],
-                             labels_out.data_ptr(), _lib.ptr(mindist), _lib.ptr(inertia_acc), _stream()), 'scd_estep')
+                             labels_out.data_ptr(), _lib.ptr(mindist), _lib.ptr(inertia_acc), int(bool(exact)),
+                             ws.data_ptr(), ws.numel(), _stream()), 'scd_estep')
 
 
 class _MStep:

@@ -51,6 +51,9 @@ def test_pairwise_distance_and_estep(n, d, k):
     assert torch.allclose(mind.cpu(), ref.min(dim=1).values, atol=ATOL, rtol=0)
     assert abs(acc.item() - ref.min(dim=1).values.double().sum().item()) < 1e-3
     assert torch.equal(kmeans.predict(X.cuda(), C.cuda()), labels)
+    exact = torch.empty_like(labels)                                           # the fp32 direct-form E-step kernel
+    kmeans._estep(X.cuda(), C.cuda(), exact, None, exact=True)
+    _assert_labels(exact, X, C)
 
 
 def test_pairwise_distance_matches_golden(golden_dir):
@@ -195,7 +198,11 @@ def test_full_size_c2_properties():
     rows = torch.randperm(cfg.n, generator=torch.Generator().manual_seed(0))[:4096]
     _assert_labels(labels[rows.cuda()], X[rows], C0)
     full = kmeans.pairwise_distance(Xd[:8192], Cd)                             # E-step == argmin of the full matrix
-    assert torch.equal(full.argmin(dim=1), labels[:8192])
+    clear = _margin_mask(full.cpu()).cuda()
+    assert clear.float().mean() > 0.99 and torch.equal(full.argmin(dim=1)[clear], labels[:8192][clear])
+    exact = torch.empty_like(labels)                                           # fp32 direct-form kernel == tensor-core kernel
+    kmeans._estep(Xd, Cd, exact, None, exact=True)
+    assert (exact == labels).float().mean() > 0.9999
     ms = kmeans._MStep(cfg.n, synth.D, cfg.k, 'cuda')
     ms.sums_counts(Xd, labels)
     assert int(ms.counts.sum()) == cfg.n

@@ -17,15 +17,17 @@ def step_kmeans():
     from oracle import kmeans_oracle
     from scd_b200 import kmeans
     torch.manual_seed(0)
-    for (n, d, k) in [(600, 64, 12), (1, 8, 1), (130, 20, 65), (1000, 768, 100), (257, 4, 3)]:
+    for (n, d, k) in [(600, 64, 12), (1, 8, 1), (130, 20, 65), (1000, 768, 100), (257, 4, 3), (5000, 768, 200), (3000, 128, 300), (2000, 64, 1000)]:
         X = torch.randn(n, d); X = X / X.norm(dim=1, keepdim=True)
         C = X[torch.randperm(n)[:k]].clone() if n >= k else torch.randn(k, d)
         ref = kmeans_oracle.pairwise_distance(X, C, None)
         got = kmeans.pairwise_distance(X.cuda(), C.cuda()).cpu()
         lab_o, mind_o, in_o = kmeans_oracle.estep(X, C)
         lab = kmeans.predict(X.cuda(), C.cuda()).cpu()
+        mind = torch.empty(n, device='cuda'); acc = torch.zeros(1, dtype=torch.float64, device='cuda'); l2 = torch.empty(n, dtype=torch.int64, device='cuda')
+        kmeans._estep(X.cuda(), C.cuda(), l2, acc, mind)
         print(f'pd n={n} d={d} k={k}: max|err|={float((ref-got).abs().max()):.3e} labels_equal={bool(torch.equal(lab, lab_o))}'
-              f' mismatches={int((lab!=lab_o).sum())}')
+              f' mismatches={int((lab!=lab_o).sum())} mindist_err={float((mind.cpu()-mind_o).abs().max()):.3e} inertia_err={abs(acc.item()-float(in_o)):.3e}')
         cen_o = kmeans_oracle.mstep(X, lab_o, C.clone())
         ms = kmeans._MStep(n, d, k, 'cuda')
         ms.sums_counts(X.cuda(), lab_o.cuda())
