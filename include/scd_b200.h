@@ -35,6 +35,9 @@ typedef uint16_t scd_bf16_t;     /* raw bfloat16 bits */
 
 SCD_API int scd_version(void);
 SCD_API const char* scd_last_error(void);
+/* Debugging aid (no reference counterpart): when non-NULL, scd_name_topk fills [pairs][16] int64 cycle
+ * counters (issuer / epilogue wait times) into this device buffer; NULL switches it off. */
+SCD_API void scd_debug_set_name_profile(void* dev_buf_pairs_x16_i64);
 
 /* ---------------------------------------------------------------- k-means (a1-a4) */
 
@@ -46,7 +49,7 @@ SCD_API int scd_pairwise_distance(const float* X, int64_t N, int D, const float*
 
 /* E-step, faster_mix_k_means_pytorch.py:58-60 / :105-107: labels = argmin_k dist (ties -> lowest k, NaN wins),
  * mindist = min_k dist, *inertia_acc += sum(mindist) (fp64 accumulator, caller zeroes it).
- * Tensor-core path (D % 4 == 0, K <= 1024, X 16-byte aligned): ||x||^2 - 2 x.c + ||c||^2 with the contraction
+ * Tensor-core path (D % 8 == 0, D >= 40, K <= 1024, X 16-byte aligned): ||x||^2 - 2 x.c + ||c||^2 with the contraction
  * issued as three bf16 tcgen05 MMAs (hi/lo split of x and c, fp32 accumulate; X is read once, as fp32).
  * Other shapes: the fp32 direct-form kernel of scd_pairwise_distance with the argmin fused (exact = 1 forces it).
  * ws holds the per-iteration centroid hi/lo planes and norms. */

@@ -17,6 +17,7 @@ _i64, _int, _f32, _sz, _vp = C.c_int64, C.c_int, C.c_float, C.c_size_t, C.c_void
 SIGNATURES = {
     'scd_version': (_int, []),
     'scd_last_error': (C.c_char_p, []),
+    'scd_debug_set_name_profile': (None, [_vp]),
     'scd_pairwise_distance': (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp]),
     'scd_estep_workspace_bytes': (_sz, [_int, _int]),
     'scd_estep': (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _int, _vp, _sz, _vp]),

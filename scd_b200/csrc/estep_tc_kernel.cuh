@@ -17,8 +17,9 @@
 // epilogue warps (thread = row) fold  ||c||^2 - 2 acc  into a running argmin, so [N, K] never exists.
 // HBM-bound while 3 * K <~ 500 (K = 100 / 120 / 200); tensor-bound for K = 1000.
 //
-// Warp roles (384 threads, 1 CTA / SM, persistent over 128-row tiles):
-//   0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle | 4-7 converters | 8-11 epilogue
+// Warp roles (512 threads, 1 CTA / SM, persistent over 128-row tiles):
+//   0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle | 4-11 converters (two sets of four warps
+//   that take alternate k-blocks, so every scheduler has two conversions in flight) | 12-15 epilogue
 #pragma once
 #include "ptx.cuh"
 #include <cuda_bf16.h>
@@ -27,23 +28,22 @@ namespace scd {
 
 constexpr int kEsBM = 128;              // rows per tile
 constexpr int kEsBK = 32;               // k per stage
-constexpr int kEsXStages = 4;           // fp32 X ring
+constexpr int kEsMaxXStages = 12;       // fp32 X ring: as deep as shared memory allows (host picks EsParams::x_stages)
 constexpr int kEsAStages = 3;           // converted hi/lo ring
 constexpr int kEsBStages = 3;           // centroid hi/lo ring
 constexpr int kEsXBytes = kEsBM * kEsBK * 4;          // 16384
 constexpr int kEsAPlane = kEsBM * kEsBK * 2;          // 8192 (one of hi / lo)
-constexpr int kEsBPlane = 256 * kEsBK * 2;            // 16384 (capacity for N = 256)
-constexpr int kEsThreads = 384;
+constexpr int kEsConvSets = 2;          // converter warp sets (4 warps each), alternating k-blocks
+constexpr int kEsThreads = 32 * (4 + 4 * kEsConvSets + 4);
 constexpr int kEsMaxK = 1024;
 
-struct EsSmem {
-  static constexpr int x_off = 0;
-  static constexpr int a_off = x_off + kEsXStages * kEsXBytes;                  // 65536
-  static constexpr int b_off = a_off + kEsAStages * 2 * kEsAPlane;              // 114688
-  static constexpr int bar_off = b_off + kEsBStages * 2 * kEsBPlane;            // 212992
-  static constexpr int x_full = bar_off;                                        // [4]
-  static constexpr int x_empty = x_full + 8 * kEsXStages;
-  static constexpr int a_full = x_empty + 8 * kEsXStages;                       // [3]
+// Dynamic shared memory: [X ring: x_stages x 16 KB][A ring: 3 x (hi, lo) x 8 KB][B ring: 3 x (hi, lo) x b_plane]
+// [tail: barriers, TMEM pointer, ||c||^2, ||x||^2 ring].  The E-step is HBM-latency bound (ncu, round 1: the
+// converters wait on x_full), so whatever the centroid ring does not need goes to X stages in flight.
+struct EsTail {
+  static constexpr int x_full = 0;                                              // [12]
+  static constexpr int x_empty = x_full + 8 * kEsMaxXStages;
+  static constexpr int a_full = x_empty + 8 * kEsMaxXStages;                    // [3]
   static constexpr int a_empty = a_full + 8 * kEsAStages;
   static constexpr int b_full = a_empty + 8 * kEsAStages;                       // [3]
   static constexpr int b_empty = b_full + 8 * kEsBStages;
@@ -51,10 +51,10 @@ struct EsSmem {
   static constexpr int t_empty = t_full + 16;
   static constexpr int tmem_ptr = t_empty + 16;
   static constexpr int cnorm = tmem_ptr + 16;                                   // [kEsMaxK] floats
-  static constexpr int xnorm = cnorm + 4 * kEsMaxK;                             // [4][128] floats
-  static constexpr int total = xnorm + 4 * 4 * kEsBM;
+  static constexpr int xnorm = cnorm + 4 * kEsMaxK;                             // [4 tiles][sets][128] floats
+  static constexpr int total = xnorm + 4 * 4 * kEsConvSets * kEsBM;
 };
-static_assert(EsSmem::total + 1024 <= 232448, "exceeds 227 KB of shared memory");
+constexpr int kEsSmemLimit = 232448;    // 227 KB opt-in maximum per CTA
 
 struct EsParams {
   long long n_rows;
@@ -63,10 +63,24 @@ struct EsParams {
   int n_ntiles;            // ceil(K / 256) (1 for K <= 256)
   int num_kb;              // ceil(D / 32)
   int n_row_tiles;
+  int x_stages;            // depth of the fp32 X ring (2 .. kEsMaxXStages)
+  int b_plane;             // bytes of one centroid plane stage: align_up(n_tile * 64, 1024)
   const float* cnorm;      // [K]
   long long* labels;       // [N]
   float* mindist;          // nullable [N]
   double* inertia;         // nullable
+};
+
+// host + device: byte offsets of the rings for a given plan
+struct EsLayout {
+  int x_off, a_off, b_off, tail_off, total;
+  __host__ __device__ EsLayout(int x_stages, int b_plane) {
+    x_off = 0;
+    a_off = x_off + x_stages * kEsXBytes;
+    b_off = a_off + kEsAStages * 2 * kEsAPlane;
+    tail_off = b_off + kEsBStages * 2 * b_plane;
+    total = tail_off + EsTail::total;
+  }
 };
 
 // fp32 centroids -> bf16 hi / lo planes [K, D] + ||c||^2
@@ -107,8 +121,10 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
   const int nkb = p.num_kb;
+  const EsLayout L(p.x_stages, p.b_plane);
+  const int kEsXStages = p.x_stages;
 
-  auto bar = [&](int base, int i) { return sbase + base + 8 * i; };
+  auto bar = [&](int base, int i) { return sbase + L.tail_off + base + 8 * i; };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_x);
@@ -116,24 +132,24 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     ptx::prefetch_tensormap(&map_clo);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kEsXStages; ++s) { ptx::mbar_init(bar(EsSmem::x_full, s), 1); ptx::mbar_init(bar(EsSmem::x_empty, s), 4); }
-    for (int s = 0; s < kEsAStages; ++s) { ptx::mbar_init(bar(EsSmem::a_full, s), 4); ptx::mbar_init(bar(EsSmem::a_empty, s), 1); }
-    for (int s = 0; s < kEsBStages; ++s) { ptx::mbar_init(bar(EsSmem::b_full, s), 1); ptx::mbar_init(bar(EsSmem::b_empty, s), 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(bar(EsSmem::t_full, b), 1); ptx::mbar_init(bar(EsSmem::t_empty, b), 4); }
+    for (int s = 0; s < kEsXStages; ++s) { ptx::mbar_init(bar(EsTail::x_full, s), 1); ptx::mbar_init(bar(EsTail::x_empty, s), 4); }
+    for (int s = 0; s < kEsAStages; ++s) { ptx::mbar_init(bar(EsTail::a_full, s), 4); ptx::mbar_init(bar(EsTail::a_empty, s), 1); }
+    for (int s = 0; s < kEsBStages; ++s) { ptx::mbar_init(bar(EsTail::b_full, s), 1); ptx::mbar_init(bar(EsTail::b_empty, s), 1); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(bar(EsTail::t_full, b), 1); ptx::mbar_init(bar(EsTail::t_empty, b), 4); }
     ptx::fence_mbar_init_cluster();
   }
   if (warp == 2) {
-    ptx::tmem_alloc<1>(sbase + EsSmem::tmem_ptr, 512);
+    ptx::tmem_alloc<1>(sbase + L.tail_off + EsTail::tmem_ptr, 512);
     ptx::tmem_relinquish<1>();
   }
   {
-    float* cn = reinterpret_cast<float*>(smem + EsSmem::cnorm);
+    float* cn = reinterpret_cast<float*>(smem + L.tail_off + EsTail::cnorm);
     for (int k = threadIdx.x; k < p.n_clusters; k += blockDim.x) cn[k] = p.cnorm[k];
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + EsSmem::tmem_ptr);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L.tail_off + EsTail::tmem_ptr);
 
   if (warp == 0) {
     // =================================================== TMA producer
@@ -143,16 +159,16 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x) {
         for (int nt = 0; nt < p.n_ntiles; ++nt) {
           for (int kb = 0; kb < nkb; ++kb) {
-            ptx::mbar_wait(bar(EsSmem::x_empty, xs), xph ^ 1, 700 + xs);
-            ptx::mbar_arrive_expect_tx(bar(EsSmem::x_full, xs), kEsXBytes);
-            ptx::tma_load_2d<1>(sbase + EsSmem::x_off + xs * kEsXBytes, &map_x, bar(EsSmem::x_full, xs), kb * kEsBK, rt * kEsBM,
+            ptx::mbar_wait(bar(EsTail::x_empty, xs), xph ^ 1, 700 + xs);
+            ptx::mbar_arrive_expect_tx(bar(EsTail::x_full, xs), kEsXBytes);
+            ptx::tma_load_2d<1>(sbase + L.x_off + xs * kEsXBytes, &map_x, bar(EsTail::x_full, xs), kb * kEsBK, rt * kEsBM,
                                 p.n_ntiles > 1 ? ptx::kEvictNormal : ptx::kEvictFirst);
             if (++xs == kEsXStages) { xs = 0; xph ^= 1; }
-            ptx::mbar_wait(bar(EsSmem::b_empty, bs), bph ^ 1, 710 + bs);
-            ptx::mbar_arrive_expect_tx(bar(EsSmem::b_full, bs), b_bytes);
-            const uint32_t bdst = sbase + EsSmem::b_off + bs * 2 * kEsBPlane;
-            ptx::tma_load_2d<1>(bdst, &map_chi, bar(EsSmem::b_full, bs), kb * kEsBK, nt * 256, ptx::kEvictLast);
-            ptx::tma_load_2d<1>(bdst + kEsBPlane, &map_clo, bar(EsSmem::b_full, bs), kb * kEsBK, nt * 256, ptx::kEvictLast);
+            ptx::mbar_wait(bar(EsTail::b_empty, bs), bph ^ 1, 710 + bs);
+            ptx::mbar_arrive_expect_tx(bar(EsTail::b_full, bs), b_bytes);
+            const uint32_t bdst = sbase + L.b_off + bs * 2 * p.b_plane;
+            ptx::tma_load_2d<1>(bdst, &map_chi, bar(EsTail::b_full, bs), kb * kEsBK, nt * 256, ptx::kEvictLast);
+            ptx::tma_load_2d<1>(bdst + p.b_plane, &map_clo, bar(EsTail::b_full, bs), kb * kEsBK, nt * 256, ptx::kEvictLast);
             if (++bs == kEsBStages) { bs = 0; bph ^= 1; }
           }
         }
@@ -166,15 +182,15 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x) {
         for (int nt = 0; nt < p.n_ntiles; ++nt, ++tile_no) {
           const uint32_t buf = tile_no & 1u;
-          ptx::mbar_wait(bar(EsSmem::t_empty, buf), ((tile_no >> 1) & 1u) ^ 1u, 720 + buf);
+          ptx::mbar_wait(bar(EsTail::t_empty, buf), ((tile_no >> 1) & 1u) ^ 1u, 720 + buf);
           ptx::tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + buf * 256;
           for (int kb = 0; kb < nkb; ++kb) {
-            ptx::mbar_wait(bar(EsSmem::a_full, as), aph, 730 + as);
-            ptx::mbar_wait(bar(EsSmem::b_full, bs), bph, 740 + bs);
+            ptx::mbar_wait(bar(EsTail::a_full, as), aph, 730 + as);
+            ptx::mbar_wait(bar(EsTail::b_full, bs), bph, 740 + bs);
             ptx::tc_fence_after_sync();
-            const uint32_t a_hi = sbase + EsSmem::a_off + as * 2 * kEsAPlane, a_lo = a_hi + kEsAPlane;
-            const uint32_t b_hi = sbase + EsSmem::b_off + bs * 2 * kEsBPlane, b_lo = b_hi + kEsBPlane;
+            const uint32_t a_hi = sbase + L.a_off + as * 2 * kEsAPlane, a_lo = a_hi + kEsAPlane;
+            const uint32_t b_hi = sbase + L.b_off + bs * 2 * p.b_plane, b_lo = b_hi + p.b_plane;
 #pragma unroll
             for (int kk = 0; kk < kEsBK / 16; ++kk) {
               const uint32_t ko = kk * 32;          // 16 bf16 = 32 bytes inside the 64-byte swizzle atom
@@ -184,34 +200,39 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
               ptx::umma_bf16<1>(d_tmem, dah, dbl, idesc, 1u);
               ptx::umma_bf16<1>(d_tmem, dal, dbh, idesc, 1u);
             }
-            ptx::umma_commit<1>(bar(EsSmem::a_empty, as), 0);
-            ptx::umma_commit<1>(bar(EsSmem::b_empty, bs), 0);
+            ptx::umma_commit<1>(bar(EsTail::a_empty, as), 0);
+            ptx::umma_commit<1>(bar(EsTail::b_empty, bs), 0);
             if (++as == kEsAStages) { as = 0; aph ^= 1; }
             if (++bs == kEsBStages) { bs = 0; bph ^= 1; }
           }
-          ptx::umma_commit<1>(bar(EsSmem::t_full, buf), 0);
+          ptx::umma_commit<1>(bar(EsTail::t_full, buf), 0);
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 4 + 4 * kEsConvSets) {
     // =================================================== converters: fp32 tile -> bf16 hi / lo operand tiles
-    const int row = (int)(warp - 4) * 32 + (int)lane;
+    // Set `cset` handles the k-blocks whose running index g (over the whole kernel) is congruent to cset.
+    const int cset = (int)(warp - 4) >> 2;
+    const int row = (int)((warp - 4) & 3) * 32 + (int)lane;
     const uint32_t x_row = (uint32_t)row * 128u, x_sw = (uint32_t)(row & 7);
     const uint32_t a_row = (uint32_t)row * 64u, a_sw = (uint32_t)((row >> 1) & 3);
-    float* xnorm_s = reinterpret_cast<float*>(smem + EsSmem::xnorm);
-    int xs = 0, as = 0; uint32_t xph = 0, aph = 0;
-    for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x) {
+    float* xnorm_s = reinterpret_cast<float*>(smem + L.tail_off + EsTail::xnorm);
+    uint32_t g = 0;                       // running k-block index: ring slots and parities derive from it
+    uint32_t my_tile = 0;                 // row tiles this CTA has converted: ||x||^2 slot = my_tile & 3
+    for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x, ++my_tile) {
       for (int nt = 0; nt < p.n_ntiles; ++nt) {
         float norm = 0.f;
-        for (int kb = 0; kb < nkb; ++kb) {
-          ptx::mbar_wait(bar(EsSmem::x_full, xs), xph, 750 + xs);
-          const uint8_t* xt = smem + EsSmem::x_off + xs * kEsXBytes + x_row;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          if ((int)(g % kEsConvSets) != cset) continue;
+          const uint32_t xs = g % kEsXStages, xph = (g / kEsXStages) & 1u;
+          const uint32_t as = g % kEsAStages, aph = (g / kEsAStages) & 1u;
+          ptx::mbar_wait(bar(EsTail::x_full, xs), xph, 750 + xs);
+          const uint8_t* xt = smem + L.x_off + xs * kEsXBytes + x_row;
           float4 f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = *reinterpret_cast<const float4*>(xt + ((((uint32_t)j) ^ x_sw) << 4));
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar(EsSmem::x_empty, xs));      // the fp32 stage is in registers
-          if (++xs == kEsXStages) { xs = 0; xph ^= 1; }
+          if (lane == 0) ptx::mbar_arrive(bar(EsTail::x_empty, xs));      // the fp32 stage is in registers
           uint4 hi[4], lo[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -230,39 +251,44 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             hi[c] = make_uint4(h[0], h[1], h[2], h[3]);
             lo[c] = make_uint4(l[0], l[1], l[2], l[3]);
           }
-          ptx::mbar_wait(bar(EsSmem::a_empty, as), aph ^ 1, 760 + as);
-          uint8_t* at = smem + EsSmem::a_off + as * 2 * kEsAPlane + a_row;
+          ptx::mbar_wait(bar(EsTail::a_empty, as), aph ^ 1, 760 + as);
+          uint8_t* at = smem + L.a_off + as * 2 * kEsAPlane + a_row;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint32_t off = (((uint32_t)c) ^ a_sw) << 4;
             *reinterpret_cast<uint4*>(at + off) = hi[c];
             *reinterpret_cast<uint4*>(at + kEsAPlane + off) = lo[c];
           }
-          if (kb == nkb - 1 && nt == 0) xnorm_s[(rt & 3) * kEsBM + row] = norm;
+          // this set's last k-block of the tile: publish its share of ||x||^2 before the a_full arrive
+          if (nt == 0 && kb + kEsConvSets >= nkb) xnorm_s[((my_tile & 3u) * kEsConvSets + cset) * kEsBM + row] = norm;
           fence_proxy_async_smem();                                       // generic-proxy writes -> visible to the tensor core
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar(EsSmem::a_full, as));
-          if (++as == kEsAStages) { as = 0; aph ^= 1; }
+          if (lane == 0) ptx::mbar_arrive(bar(EsTail::a_full, as));
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 4 + 4 * kEsConvSets) {
     // =================================================== epilogue: running argmin per row
     const uint32_t quad = warp & 3u;
     const int row_in_tile = (int)quad * 32 + (int)lane;
     const uint32_t lane_addr = (quad * 32u) << 16;
-    const float* cn = reinterpret_cast<const float*>(smem + EsSmem::cnorm);
-    const float* xnorm_s = reinterpret_cast<const float*>(smem + EsSmem::xnorm);
-    uint32_t tile_no = 0;
+    const float* cn = reinterpret_cast<const float*>(smem + L.tail_off + EsTail::cnorm);
+    const float* xnorm_s = reinterpret_cast<const float*>(smem + L.tail_off + EsTail::xnorm);
+    uint32_t tile_no = 0, my_tile = 0;
     double inertia_local = 0.0;
-    for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x) {
+    // the converters run at most 2 accumulator tiles + 3 operand stages ahead of this warp, so the
+    // 4-deep ||x||^2 ring (slot = row tiles done & 3) is never overwritten before it is read
+    for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x, ++my_tile) {
       float best = INFINITY; int best_k = -1;
       float xn = 0.f;
       for (int nt = 0; nt < p.n_ntiles; ++nt, ++tile_no) {
         const uint32_t buf = tile_no & 1u;
-        ptx::mbar_wait(bar(EsSmem::t_full, buf), (tile_no >> 1) & 1u, 770 + buf);
+        ptx::mbar_wait(bar(EsTail::t_full, buf), (tile_no >> 1) & 1u, 770 + buf);
         ptx::tc_fence_after_sync();
-        if (nt == 0) xn = xnorm_s[(rt & 3) * kEsBM + row_in_tile];
+        if (nt == 0) {
+#pragma unroll
+          for (int cs = 0; cs < kEsConvSets; ++cs) xn += xnorm_s[((my_tile & 3u) * kEsConvSets + cs) * kEsBM + row_in_tile];
+        }
         const uint32_t taddr = tmem_base + lane_addr + buf * 256;
         const int k0 = nt * 256;
         const int n_here = min(p.n_clusters - k0, 256);
@@ -282,7 +308,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
         ptx::tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar(EsSmem::t_empty, buf));
+        if (lane == 0) ptx::mbar_arrive(bar(EsTail::t_empty, buf));
       }
       const long long row = (long long)rt * kEsBM + row_in_tile;
       if (row < p.n_rows) {

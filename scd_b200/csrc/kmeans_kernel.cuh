@@ -220,13 +220,14 @@ __global__ void label_scatter_kernel(const long long* __restrict__ labels, long 
 // end of the chunk, the warp flushes with vector reductions (red.global.add.v4.f32) into sums[k].
 // Atomics per (cluster, column) ~ rows_in_cluster / kSegRows instead of rows_in_cluster.
 // --------------------------------------------------------------------------------------------
-constexpr int kSegRows = 64;
+constexpr int kSegRows = 32;       // one row id per lane: the chunk's order[] entries arrive in one coalesced load
 constexpr int kSegMaxVec = 8;      // supports D <= 1024 (D % 4 == 0)
 
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+template <int NV>     // register capacity in float4 per lane (NV * 128 >= D rounded down to 128); 2 / 4 / 6 / 8
 __global__ void __launch_bounds__(256)
 segment_sum_kernel(const float* __restrict__ X, const int* __restrict__ order, const int* __restrict__ offsets,
                    int K, int D, float* __restrict__ sums) {
@@ -238,39 +239,42 @@ segment_sum_kernel(const float* __restrict__ X, const int* __restrict__ order, c
   const int p1 = min(p0 + kSegRows, total);
   const int nvec = D >> 7;                       // float4 per lane for the 128-column-aligned part
   const int tail = D - (nvec << 7);              // < 128 remaining columns (multiple of 4)
+  const int my_row = (p0 + lane < p1) ? order[p0 + lane] : 0;
   // cluster of the first position: binary search in offsets
   int lo = 0, hi = K;
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offsets[mid] <= p0) lo = mid; else hi = mid; }
   int k = lo;
   while (k < K - 1 && offsets[k + 1] <= p0) ++k;   // skip empty clusters
-  float4 acc[kSegMaxVec];
+  float4 acc[NV], cur[NV], nxt[NV];
 #pragma unroll
-  for (int j = 0; j < kSegMaxVec; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 acc_tail = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc_tail = make_float4(0.f, 0.f, 0.f, 0.f), cur_tail = acc_tail, nxt_tail = acc_tail;
   const bool tail_lane = (lane * 4) < tail;
 
   auto flush = [&](int kk) {
     float* dst = sums + (long long)kk * D;
 #pragma unroll
-    for (int j = 0; j < kSegMaxVec; ++j)
+    for (int j = 0; j < NV; ++j)
       if (j < nvec) { red_add_v4(dst + j * 128 + lane * 4, acc[j]); acc[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
     if (tail_lane) { red_add_v4(dst + nvec * 128 + lane * 4, acc_tail); acc_tail = make_float4(0.f, 0.f, 0.f, 0.f); }
   };
+  auto load_row = [&](int p, float4 (&dst)[NV], float4& dst_tail) {
+    const float* src = X + (long long)__shfl_sync(0xffffffffu, my_row, p - p0) * D;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      if (j < nvec) dst[j] = __ldg(reinterpret_cast<const float4*>(src + j * 128 + lane * 4));
+    if (tail_lane) dst_tail = __ldg(reinterpret_cast<const float4*>(src + nvec * 128 + lane * 4));
+  };
 
   int seg_end = offsets[k + 1];
+  load_row(p0, cur, cur_tail);
   for (int p = p0; p < p1; ++p) {
+    if (p + 1 < p1) load_row(p + 1, nxt, nxt_tail);          // next row in flight while this one is added
     while (p >= seg_end) { flush(k); ++k; seg_end = offsets[k + 1]; }
-    const float* src = X + (long long)order[p] * D;
 #pragma unroll
-    for (int j = 0; j < kSegMaxVec; ++j)
-      if (j < nvec) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src + j * 128 + lane * 4));
-        acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
-      }
-    if (tail_lane) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(src + nvec * 128 + lane * 4));
-      acc_tail.x += v.x; acc_tail.y += v.y; acc_tail.z += v.z; acc_tail.w += v.w;
-    }
+    for (int j = 0; j < NV; ++j)
+      if (j < nvec) { acc[j].x += cur[j].x; acc[j].y += cur[j].y; acc[j].z += cur[j].z; acc[j].w += cur[j].w; cur[j] = nxt[j]; }
+    if (tail_lane) { acc_tail.x += cur_tail.x; acc_tail.y += cur_tail.y; acc_tail.z += cur_tail.z; acc_tail.w += cur_tail.w; cur_tail = nxt_tail; }
   }
   flush(k);
 }

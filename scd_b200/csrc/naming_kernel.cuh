@@ -17,8 +17,13 @@
 // those k parked chunks at the end of the vocabulary sweep finishes the row.  (The unsupervised
 // driver's softmax additionally keeps a running max / sum-exp.)  Only [N, k] leaves the SM.
 //
-// Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer (leader CTA only), 2 = TMEM
-// allocator, 3 = idle, 4..7 = epilogue (TMEM lane quadrant = warp & 3).
+// Warp roles (384 threads): 0 = vocabulary (B) TMA producer, 1 = MMA issuer (leader CTA only), 2 = TMEM
+// allocator, 3 = image-row (A) TMA producer, 4..11 = epilogue (TMEM lane quadrant = warp & 3; warps
+// 4..7 take columns 0..127 of every accumulator tile, warps 8..11 columns 128..255, so each scheduler
+// has two epilogue warps to interleave).  The single-thread issue loops (MMA, TMA) probe the NEXT
+// stage's mbarrier with a non-blocking test_wait before they issue the current stage's work, so the
+// ~100-cycle barrier round trip is off the critical path (ncu, round 1: the issuer, not the tensor
+// pipe, was the bottleneck at 55 % tensor-active).
 #pragma once
 #include "ptx.cuh"
 #include <cuda_bf16.h>
@@ -34,7 +39,8 @@ constexpr int kBK = 32;                // k per B stage            (64 B rows, S
 constexpr int kBStages = 4;
 constexpr int kABlockBytes = kBlockM * kAKBlock * 2;     // 16384
 constexpr int kBStageBytes = (kTileN / 2) * kBK * 2;     // 8192 per CTA
-constexpr int kNameThreads = 256;
+constexpr int kNameThreads = 384;
+constexpr int kEpiHalves = 2;           // column halves of a tile, one epilogue warp set each
 constexpr int kTmemCols = 512;
 
 struct NameSmem {
@@ -66,13 +72,14 @@ struct NameParams {
   int num_kb;              // ceil(D / 64) live A k-blocks (TMA zero-fills the ragged end of D)
   int want_softmax;
   float scale_log2e;       // scale * log2(e) for the running sum-exp
-  // partial results, one slot per vocabulary chunk: [n_vsplit][N][KT] / [n_vsplit][N]
+  // partial results, one slot per (vocabulary chunk, column half): [n_vsplit * 2][N][KT] / [n_vsplit * 2][N]
   // (part_idx is pre-set to -1: slots a row never writes are skipped by the merge)
   float* part_val;
   int* part_idx;
   float* part_max;
   float* part_sum;
-  float* scratch;          // [gridDim.x][128 rows][KT slots][32] parked chunks
+  float* scratch;          // [gridDim.x][2 halves][128 rows][KT slots][32] parked chunks
+  long long* prof;         // nullable: [pairs][16] cycle counters (scd_debug_set_name_profile), debugging aid
 };
 
 // One sorted top-KT list in registers, ordered by (value descending, column ascending) - the order
@@ -103,9 +110,9 @@ struct TopK {
   }
 };
 
-// The KT chunks (32 consecutive columns) with the largest chunk maxima seen so far, sorted by maximum
-// (strict '>' on insertion: among equal maxima the earlier chunk stays in front).  slot[] says which
-// scratch slot holds the chunk's 32 values, col[] its first column.
+// The KT chunks (32 consecutive columns) with the largest chunk maxima seen so far, sorted by (maximum
+// descending, first column ascending) - an order that does not depend on the sequence in which chunks are
+// visited.  slot[] says which scratch slot holds the chunk's 32 values, col[] its first column.
 template <int KT>
 struct ChunkTop {
   float m[KT];
@@ -115,13 +122,15 @@ struct ChunkTop {
 #pragma unroll
     for (int j = 0; j < KT; ++j) { m[j] = -INFINITY; slot[j] = j; col[j] = -1; }
   }
-  __device__ __forceinline__ float floor_val() const { return m[KT - 1]; }
+  __device__ __forceinline__ bool admits(float cmax, int colbase) const {
+    return cmax > m[KT - 1] || (cmax == m[KT - 1] && colbase < col[KT - 1]);
+  }
   // the caller has already parked the chunk in slot[KT-1]
   __device__ __forceinline__ void insert_last(float cmax, int colbase) {
     m[KT - 1] = cmax; col[KT - 1] = colbase;
 #pragma unroll
     for (int j = KT - 1; j > 0; --j) {
-      if (m[j] > m[j - 1]) {
+      if (m[j] > m[j - 1] || (m[j] == m[j - 1] && col[j] < col[j - 1])) {
         float tm = m[j]; m[j] = m[j - 1]; m[j - 1] = tm;
         int ts = slot[j]; slot[j] = slot[j - 1]; slot[j - 1] = ts;
         int tc = col[j]; col[j] = col[j - 1]; col[j - 1] = tc;
@@ -164,7 +173,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     for (int kb = 0; kb < kNumAKBlocks; ++kb) { ptx::mbar_init(a_full_bar(kb), 1); ptx::mbar_init(a_empty_bar(kb), 1); }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(tmem_full_bar(b), 1);
-      ptx::mbar_init(tmem_empty_bar(b), 8);      // 4 epilogue warps x 2 CTAs arrive on the leader's copy
+      ptx::mbar_init(tmem_empty_bar(b), 16);     // 8 epilogue warps x 2 CTAs arrive on the leader's copy
     }
     ptx::fence_mbar_init_cluster();
   }
@@ -187,95 +196,131 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     int t1 = min(t0 + p.tiles_per_chunk, tiles_total);
     return max(t1 - t0, 0);
   };
+  // Staggered sweep: pair q starts its walk over an item's tiles at a different offset and wraps around, so
+  // at any moment the 74 pairs read 74 different vocabulary tiles (spread over all L2 slices) instead of
+  // all hammering the same 16 KB.  The result does not depend on the visiting order (explicit tie rules).
+  auto item_tile = [&](int it, int t) {
+    const int nt = item_ntiles(it);
+    const int start = (int)(((long long)pair * nt) / n_pairs);
+    int tt = t + start;
+    if (tt >= nt) tt -= nt;
+    return item_tile0(it) + tt;
+  };
 
   if (warp == 0) {
-    // ======================================================= TMA producer (one lane)
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int my_item_no = 0;                       // how many items this pair has started (A buffer reuse count)
-      auto load_a = [&](int it, int reuse, int kb) {
-        ptx::mbar_wait(a_empty_bar(kb), (reuse & 1) ^ 1, 100 + kb);
-        if (leader) ptx::mbar_arrive_expect_tx(a_full_bar(kb), 2 * kABlockBytes);
-        const int row0 = item_rb(it) * 2 * kBlockM + (int)cta_rank * kBlockM;
-        ptx::tma_load_2d<2>(sbase + NameSmem::a_off + kb * kABlockBytes, &map_x,
-                            a_full_bar(kb) & ptx::kPeerBitMask, kb * kAKBlock, row0, ptx::kEvictFirst);
-      };
-      for (int it = pair; it < n_items; it += n_pairs, ++my_item_no) {
-        if (my_item_no == 0) {
-          for (int kb = 0; kb < nkb; ++kb) load_a(it, 0, kb);
-        }
-        const int nt = item_ntiles(it);
-        const int next_it = it + n_pairs;
-        const bool has_next = next_it < n_items;
-        for (int t = 0; t < nt; ++t) {
-          const int v0 = (item_tile0(it) + t) * kTileN + (int)cta_rank * (kTileN / 2);
-          const bool last_tile = (t == nt - 1);
-          for (int kb = 0; kb < nkb; ++kb) {
-#pragma unroll
-            for (int h = 0; h < kAKBlock / kBK; ++h) {
-              ptx::mbar_wait(empty_bar(stage), phase ^ 1, 200 + stage);
-              if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * kBStageBytes);
-              ptx::tma_load_2d<2>(sbase + NameSmem::b_off + stage * kBStageBytes, &map_w,
-                                  full_bar(stage) & ptx::kPeerBitMask, kb * kAKBlock + h * kBK, v0, ptx::kEvictLast);
-              if (++stage == kBStages) { stage = 0; phase ^= 1; }
-            }
-            // the A block two steps back was released by the MMAs we just queued behind: refill it
-            // with the next item's rows while this item's last tile is still running
-            if (last_tile && has_next && kb >= 2) load_a(next_it, my_item_no + 1, kb - 2);
+    // ======================================================= vocabulary (B) TMA producer
+    // Whole warp runs the loop (warp-uniform control flow keeps addresses in uniform registers); one
+    // elected lane issues.  `free_next` is a non-blocking probe of the next stage's empty barrier made
+    // before this stage's TMA goes out.
+    static_assert(kBStages % 2 == 0 && kAKBlock == 2 * kBK, "the B ring is consumed two stages (one k-block) at a time");
+    // Refill is per stage (a slot is reloaded the moment its two MMAs retire), consumption per k-block.
+    int stage = 0; uint32_t phase = 0;
+    for (int it = pair; it < n_items; it += n_pairs) {
+      const int nt = item_ntiles(it);
+      for (int t = 0; t < nt; ++t) {
+        const int v0 = item_tile(it, t) * kTileN + (int)cta_rank * (kTileN / 2);
+        for (int ks = 0; ks < nkb * (kAKBlock / kBK); ++ks) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1, 200 + stage);
+          if (ptx::elect_one()) {
+            if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * kBStageBytes);
+            ptx::tma_load_2d<2>(sbase + NameSmem::b_off + stage * kBStageBytes, &map_w,
+                                full_bar(stage) & ptx::kPeerBitMask, ks * kBK, v0, ptx::kEvictLast);
           }
-        }
-        if (has_next) {
-          const int first_left = nt == 0 ? 0 : max(nkb - 2, 0);
-          for (int kb = first_left; kb < nkb; ++kb) load_a(next_it, my_item_no + 1, kb);
+          __syncwarp();
+          if (++stage == kBStages) { stage = 0; phase ^= 1; }
         }
       }
     }
+  } else if (warp == 3) {
+    // ======================================================= image-row (A) TMA producer
+    // The pair's 256 rows stay in shared memory for a whole work item; k-block kb of the NEXT item is
+    // loaded as soon as the last tile of the current item has consumed it (a_empty, committed by the MMA
+    // issuer), i.e. while that last tile is still running.
+    int my_item_no = 0;
+    for (int it = pair; it < n_items; it += n_pairs, ++my_item_no) {
+      const int row0 = item_rb(it) * 2 * kBlockM + (int)cta_rank * kBlockM;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(a_empty_bar(kb), (my_item_no & 1) ^ 1, 100 + kb);
+        if (ptx::elect_one()) {
+          if (leader) ptx::mbar_arrive_expect_tx(a_full_bar(kb), 2 * kABlockBytes);
+          ptx::tma_load_2d<2>(sbase + NameSmem::a_off + kb * kABlockBytes, &map_x,
+                              a_full_bar(kb) & ptx::kPeerBitMask, kb * kAKBlock, row0, ptx::kEvictFirst);
+        }
+        __syncwarp();
+      }
+    }
   } else if (warp == 1) {
-    // ======================================================= MMA issuer (leader CTA, one lane)
-    if (leader && lane == 0) {
+    // ======================================================= MMA issuer (leader CTA; one elected lane issues)
+    if (leader) {
       const uint32_t idesc = ptx::make_idesc_bf16_f32(2 * kBlockM, kTileN);
       int stage = 0; uint32_t phase = 0;
       uint32_t tile_no = 0;
       int my_item_no = 0;
+      const bool prof = p.prof != nullptr;
+      long long pf_t0 = prof ? clock64() : 0, pf_te = 0, pf_a = 0, pf_b = 0;
       for (int it = pair; it < n_items; it += n_pairs, ++my_item_no) {
         const int nt = item_ntiles(it);
         for (int t = 0; t < nt; ++t, ++tile_no) {
           const uint32_t buf = tile_no & 1u;
-          ptx::mbar_wait(tmem_empty_bar(buf), ((tile_no >> 1) & 1u) ^ 1u, 300 + buf);
-          ptx::tc_fence_after_sync();
+          { const long long c0 = prof ? clock64() : 0;
+            ptx::mbar_wait(tmem_empty_bar(buf), ((tile_no >> 1) & 1u) ^ 1u, 300 + buf);
+            if (prof) pf_te += clock64() - c0; }
           const uint32_t d_tmem = tmem_base + buf * kTileN;
           for (int kb = 0; kb < nkb; ++kb) {
-            if (t == 0) { ptx::mbar_wait(a_full_bar(kb), my_item_no & 1, 400 + kb); ptx::tc_fence_after_sync(); }
+            if (t == 0) { const long long c0 = prof ? clock64() : 0;
+              ptx::mbar_wait(a_full_bar(kb), my_item_no & 1, 400 + kb);
+              if (prof) pf_a += clock64() - c0; }
             const uint32_t a_addr = sbase + NameSmem::a_off + kb * kABlockBytes;
+            // one k-block = two B stages: both full barriers are probed together, then four MMAs go out
+            { const long long c0 = prof ? clock64() : 0;
+              ptx::mbar_wait2(full_bar(stage), full_bar(stage + 1), phase, 500 + stage);
+              if (prof) pf_b += clock64() - c0; }
+            ptx::tc_fence_after_sync();
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int h = 0; h < kAKBlock / kBK; ++h) {
-              ptx::mbar_wait(full_bar(stage), phase, 500 + stage);
-              ptx::tc_fence_after_sync();
-              const uint32_t b_addr = sbase + NameSmem::b_off + stage * kBStageBytes;
+              for (int h = 0; h < 2; ++h) {
+                const uint32_t b_addr = sbase + NameSmem::b_off + (stage + h) * kBStageBytes;
 #pragma unroll
-              for (int kk = 0; kk < kBK / 16; ++kk) {
-                const uint64_t adesc = ptx::make_kmajor_desc(a_addr + (h * kBK + kk * 16) * 2, 128);
-                const uint64_t bdesc = ptx::make_kmajor_desc(b_addr + kk * 16 * 2, 64);
-                ptx::umma_bf16<2>(d_tmem, adesc, bdesc, idesc, (kb | h | kk) != 0 ? 1u : 0u);
+                for (int kk = 0; kk < kBK / 16; ++kk) {
+                  const uint64_t adesc = ptx::make_kmajor_desc(a_addr + (h * kBK + kk * 16) * 2, 128);
+                  const uint64_t bdesc = ptx::make_kmajor_desc(b_addr + kk * 16 * 2, 64);
+                  ptx::umma_bf16<2>(d_tmem, adesc, bdesc, idesc, (kb | h | kk) != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit<2>(empty_bar(stage + h), 0b11);
               }
-              ptx::umma_commit<2>(empty_bar(stage), 0b11);
-              if (++stage == kBStages) { stage = 0; phase ^= 1; }
+              if (t == nt - 1) ptx::umma_commit<2>(a_empty_bar(kb), 0b11);
+              if (kb == nkb - 1) ptx::umma_commit<2>(tmem_full_bar(buf), 0b11);
             }
-            if (t == nt - 1) ptx::umma_commit<2>(a_empty_bar(kb), 0b11);
+            __syncwarp();
+            stage += 2;
+            if (stage == kBStages) { stage = 0; phase ^= 1; }
           }
-          ptx::umma_commit<2>(tmem_full_bar(buf), 0b11);
         }
-        if (nt == 0) { for (int kb = 0; kb < nkb; ++kb) { ptx::mbar_wait(a_full_bar(kb), my_item_no & 1, 450 + kb); ptx::umma_commit<2>(a_empty_bar(kb), 0b11); } }
+        if (nt == 0) {       // an item without tiles still has to hand its A buffers back
+          for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_wait(a_full_bar(kb), my_item_no & 1, 450 + kb);
+            if (ptx::elect_one()) ptx::umma_commit<2>(a_empty_bar(kb), 0b11);
+            __syncwarp();
+          }
+        }
+      }
+      if (prof && lane == 0) {
+        long long* o = p.prof + (size_t)pair * 16;
+        o[0] = clock64() - pf_t0; o[1] = pf_te; o[2] = pf_a; o[3] = pf_b; o[4] = 0; o[5] = tile_no;
       }
     }
   } else if (warp >= 4) {
     // ======================================================= epilogue: one thread per image row
-    const uint32_t quad = warp & 3u;
+    const uint32_t quad = warp & 3u;                 // TMEM lane quadrant this warp may read
+    const uint32_t half = (warp - 4u) >> 2;          // column half of every tile this warp scans
     const uint32_t lane_addr = (quad * 32u) << 16;
+    constexpr int kHalfCols = kTileN / kEpiHalves;   // 128
     uint32_t tile_no = 0;
     ChunkTop<KT> ctop;
     float4* const my_scratch = reinterpret_cast<float4*>(p.scratch) +
-                               ((size_t)blockIdx.x * kBlockM + quad * 32 + lane) * KT * 8;   // KT slots x 8 float4
+                               (((size_t)blockIdx.x * kEpiHalves + half) * kBlockM + quad * 32 + lane) * KT * 8;   // KT slots x 8 float4
+    const bool prof = p.prof != nullptr && warp == 4 && leader;
+    long long pf_t0 = prof ? clock64() : 0, pf_w = 0, pf_fin = 0;
     for (int it = pair; it < n_items; it += n_pairs) {
       const int nt = item_ntiles(it);
       const long long row = (long long)item_rb(it) * 2 * kBlockM + cta_rank * kBlockM + quad * 32 + lane;
@@ -302,7 +347,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           for (int j = 0; j < 32; ++j) acc += exp2f((__uint_as_float(r[j]) - run_max) * p.scale_log2e);
           run_sum += acc;
         }
-        if (cmax > ctop.floor_val()) {
+        if (ctop.admits(cmax, colbase)) {
           float4* dst = my_scratch + ctop.slot[KT - 1] * 8;
 #pragma unroll
           for (int q = 0; q < 8; ++q)
@@ -314,56 +359,87 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
       for (int t = 0; t < nt; ++t, ++tile_no) {
         const uint32_t buf = tile_no & 1u;
-        const int col0 = (item_tile0(it) + t) * kTileN;
-        const int n_valid = (int)min((long long)kTileN, p.v_total - col0);
-        ptx::mbar_wait(tmem_full_bar(buf), (tile_no >> 1) & 1u, 600 + buf);
+        const int col0 = item_tile(it, t) * kTileN + (int)half * kHalfCols;
+        const int n_valid = (int)min((long long)kHalfCols, p.v_total - col0);      // may be <= 0 on the last tile
+        { const long long c0 = prof ? clock64() : 0;
+          ptx::mbar_wait(tmem_full_bar(buf), (tile_no >> 1) & 1u, 600 + buf);
+          if (prof) pf_w += clock64() - c0; }
         ptx::tc_fence_after_sync();
-        const uint32_t taddr = tmem_base + lane_addr + buf * kTileN;
+        const uint32_t taddr = tmem_base + lane_addr + buf * kTileN + half * kHalfCols;
         uint32_t ra[32], rb[32];
         ptx::tmem_ld_32x32(taddr, ra);
 #pragma unroll 1
-        for (int c = 0; c < kTileN / 32; c += 2) {
+        for (int c = 0; c < kHalfCols / 32; c += 2) {
           ptx::tmem_ld_wait(ra);                                 // ra = chunk c
           ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);          // in flight while ra is processed
           process(ra, col0 + c * 32, n_valid - c * 32);
           ptx::tmem_ld_wait(rb);                                 // rb = chunk c + 1
-          if (c + 2 < kTileN / 32) {
+          if (c + 2 < kHalfCols / 32) {
             ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
           } else {
-            // every column of this accumulator buffer is in registers: hand it back to the MMA issuer
+            // this warp's share of the accumulator buffer is in registers: hand it back to the MMA issuer
             ptx::tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_cluster(tmem_empty_bar(buf) & ptx::kPeerBitMask);
+            if (lane == 0) ptx::mbar_arrive_remote(tmem_empty_bar(buf) & ptx::kPeerBitMask);
           }
           process(rb, col0 + (c + 1) * 32, n_valid - (c + 1) * 32);
         }
       }
 
-      // exact top-k of the row from its (at most KT) parked chunks
+      // Exact top-k of the row from its (at most KT) parked chunks, in two divergence-free passes (a naive
+      // "push every element" scan costs ~17k warp-instructions because the 32 rows of a warp accept at
+      // different positions; it stalled the tensor pipe for ~90k cycles per work item):
+      //  1. every parked chunk contributes its own maximum, so the k-th best element is at least the
+      //     smallest parked maximum; elements below it are dropped, survivors (typically 5-10 of 160) are
+      //     appended to a per-thread candidate list in local memory with predicated stores;
+      //  2. the warp walks the candidate lists in lock step (trip count = longest list in the warp).
+      const long long pf_c1 = prof ? clock64() : 0;
       TopK<KT> top;
       top.reset();
+      {
+        float cand_v[KT * 32];
+        int cand_i[KT * 32];
+        int nc = 0;
+        const float keep_from = ctop.m[KT - 1];
+#pragma unroll
+        for (int e = 0; e < KT; ++e) {
+          const int col_e = ctop.col[e];
+          const float4* src = my_scratch + ctop.slot[e] * 8;
+          float4 x[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) x[q] = col_e >= 0 ? src[q] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float xv[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              if (col_e >= 0 && xv[w] >= keep_from && xv[w] > -INFINITY) { cand_v[nc] = xv[w]; cand_i[nc] = col_e + 4 * q + w; ++nc; }
+            }
+          }
+        }
+        int nmax = nc;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, off));
 #pragma unroll 1
-      for (int e = 0; e < KT; ++e) {
-        // register arrays cannot be indexed dynamically: select entry e with an unrolled scan
-        int slot_e = 0, col_e = -1;
-#pragma unroll
-        for (int j = 0; j < KT; ++j) if (j == e) { slot_e = ctop.slot[j]; col_e = ctop.col[j]; }
-        if (col_e < 0) continue;
-        const float4* src = my_scratch + slot_e * 8;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 x = src[q];
-          top.push(x.x, col_e + 4 * q); top.push(x.y, col_e + 4 * q + 1);
-          top.push(x.z, col_e + 4 * q + 2); top.push(x.w, col_e + 4 * q + 3);
+        for (int c = 0; c < nmax; ++c) {
+          const bool live = c < nc;
+          const float v = live ? cand_v[c] : -INFINITY;
+          const int ix = live ? cand_i[c] : -1;
+          top.push(v, ix);
         }
       }
       if (row < p.n_rows) {
-        const long long slot = (long long)item_chunk(it) * p.n_rows + row;
+        const long long slot = (long long)(item_chunk(it) * kEpiHalves + (int)half) * p.n_rows + row;
 #pragma unroll
         for (int j = 0; j < KT; ++j) { p.part_val[slot * KT + j] = top.v[j]; p.part_idx[slot * KT + j] = top.i[j]; }
         p.part_max[slot] = run_max;
         p.part_sum[slot] = run_sum;
       }
+      if (prof) pf_fin += clock64() - pf_c1;
+    }
+    if (prof && lane == 0) {
+      long long* o = p.prof + (size_t)pair * 16;
+      o[8] = clock64() - pf_t0; o[9] = pf_w; o[10] = pf_fin;
     }
   }
 

@@ -66,6 +66,24 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+// same, without the cluster-scope release fence (ERRBAR + CGAERRBAR: it drains every outstanding global
+// store of the thread first).  Enough when the only thing ordered before the arrive is tcgen05 traffic,
+// which tcgen05.wait::ld / tcgen05.fence::before_thread_sync already order.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// non-blocking probe (test_wait never suspends the thread): used to look one pipeline stage ahead
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -74,6 +92,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Two barriers probed by one statement: both try_waits are in flight before either predicate is read, so
+// the ~100-cycle barrier round trips overlap (a single-thread issue loop pays the latency once per pair).
+__device__ __forceinline__ bool mbar_try_wait2(uint32_t bar0, uint32_t bar1, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%2], %3;\n\t"
+      "and.pred p, p, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar0), "r"(bar1), "r"(parity)
       : "memory");
   return ok != 0;
 }
@@ -90,6 +123,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3FFu) == 0 && globaltimer_ns() - t0 > 4000000000ull) mbar_timeout_trap(bar, parity, tag);
+  }
+}
+
+__device__ __forceinline__ void mbar_wait2(uint32_t bar0, uint32_t bar1, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait2(bar0, bar1, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait2(bar0, bar1, parity)) {
+    if ((++spins & 0x3FFu) == 0 && globaltimer_ns() - t0 > 4000000000ull) mbar_timeout_trap(bar0, parity, tag);
   }
 }
 

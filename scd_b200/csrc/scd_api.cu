@@ -22,6 +22,7 @@
 namespace {
 
 thread_local std::string g_last_error;
+long long* g_name_prof = nullptr;      // scd_debug_set_name_profile
 
 int fail(const char* fmt, ...) {
   char buf[512];
@@ -133,12 +134,12 @@ bool plan_naming(int64_t N, int64_t V, int k, NamePlan* pl) {
   const long long items = pl->n_full_rb + (long long)tail_rb * pl->n_vsplit;
   pl->n_pairs = (int)std::max<long long>(1, std::min<long long>(pairs_hw, items));
   size_t o = 0;
-  const size_t slots = (size_t)pl->n_vsplit * (size_t)N;
+  const size_t slots = (size_t)pl->n_vsplit * scd::kEpiHalves * (size_t)N;      // one partial list per (chunk, column half)
   pl->off_val = o; o = align_up(o + slots * pl->kt * sizeof(float), 256);
   pl->off_idx = o; pl->idx_bytes = slots * pl->kt * sizeof(int); o = align_up(o + pl->idx_bytes, 256);
   pl->off_max = o; o = align_up(o + slots * sizeof(float), 256);
   pl->off_sum = o; o = align_up(o + slots * sizeof(float), 256);
-  pl->off_scratch = o; o = align_up(o + (size_t)2 * pairs_hw * scd::kBlockM * pl->kt * 32 * sizeof(float), 256);
+  pl->off_scratch = o; o = align_up(o + (size_t)2 * pairs_hw * scd::kEpiHalves * scd::kBlockM * pl->kt * 32 * sizeof(float), 256);
   pl->bytes = std::max<size_t>(o, 256);
   return true;
 }
@@ -161,6 +162,8 @@ int launch_name_topk(const CUtensorMap& mx, const CUtensorMap& mw, const scd::Na
 extern "C" {
 
 int scd_version(void) { return 100; }
+
+void scd_debug_set_name_profile(void* dev_buf_pairs_x16_i64) { g_name_prof = reinterpret_cast<long long*>(dev_buf_pairs_x16_i64); }
 
 const char* scd_last_error(void) { return g_last_error.c_str(); }
 
@@ -187,7 +190,9 @@ int scd_estep(const float* X, int64_t N, int D, const float* C, int K, int64_t* 
   if (N == 0) return 0;
   if (!X || !C || !labels) return fail("scd_estep: null pointer");
   cudaStream_t st = as_stream(stream);
-  const bool tc_ok = !exact && D % 4 == 0 && K <= scd::kEsMaxK && N < (1ll << 31) &&
+  // TMA needs 16-byte row pitches: fp32 X (D % 4) and the bf16 centroid planes (D % 8); every converter
+  // warp set must own at least one k-block per tile (it publishes its share of ||x||^2 there)
+  const bool tc_ok = !exact && D % 8 == 0 && D > scd::kEsBK * (scd::kEsConvSets - 1) && K <= scd::kEsMaxK && N < (1ll << 31) &&
                      (reinterpret_cast<uintptr_t>(X) & 15) == 0 && ws && ws_bytes >= scd_estep_workspace_bytes(K, D);
   if (!tc_ok) {
     dim3 grid((unsigned)((N + scd::kDistBM - 1) / scd::kDistBM));
@@ -219,11 +224,18 @@ int scd_estep(const float* X, int64_t N, int D, const float* C, int K, int64_t* 
   if (int e = make_map_2d(&mx, X, (uint64_t)N, (uint64_t)D, scd::kEsBM, scd::kEsBK, CU_TENSOR_MAP_SWIZZLE_128B, true)) return e;
   if (int e = make_map_2d(&mhi, chi, (uint64_t)K, (uint64_t)D, (uint32_t)p.n_tile, scd::kEsBK, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
   if (int e = make_map_2d(&mlo, clo, (uint64_t)K, (uint64_t)D, (uint32_t)p.n_tile, scd::kEsBK, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
-  static bool attr_set = false;
-  const int smem = scd::EsSmem::total + 1024;
-  if (!attr_set) {
+  // shared-memory plan: the centroid ring takes what n_tile needs, the rest goes to fp32 X stages in flight
+  p.b_plane = (int)align_up((size_t)p.n_tile * scd::kEsBK * 2, 1024);
+  {
+    const int fixed = scd::EsLayout(0, p.b_plane).total + 1024;
+    p.x_stages = std::max(2, std::min(scd::kEsMaxXStages, (scd::kEsSmemLimit - fixed) / scd::kEsXBytes));
+  }
+  const int smem = scd::EsLayout(p.x_stages, p.b_plane).total + 1024;
+  if (smem > scd::kEsSmemLimit) return fail("scd_estep: shared-memory plan does not fit (%d bytes)", smem);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
     SCD_CUDA(cudaFuncSetAttribute(scd::estep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_smem = smem;
   }
   const int grid = std::min(device_sm_count(), p.n_row_tiles);
   scd::estep_tc_kernel<<<grid, scd::kEsThreads, smem, st>>>(mx, mhi, mlo, p);
@@ -282,7 +294,11 @@ int scd_mstep_sums(const float* X, const int64_t* labels, int64_t N, int D, int 
   if (N > 0 && vec_ok) {
     const long long warps = (N + scd::kSegRows - 1) / scd::kSegRows;
     const long long blocks = (warps * 32 + 255) / 256;
-    scd::segment_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, order, offsets, K, D, sums);
+    const int nvec = D >> 7;
+    if (nvec <= 2) scd::segment_sum_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(X, order, offsets, K, D, sums);
+    else if (nvec <= 4) scd::segment_sum_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(X, order, offsets, K, D, sums);
+    else if (nvec <= 6) scd::segment_sum_kernel<6><<<(unsigned)blocks, 256, 0, st>>>(X, order, offsets, K, D, sums);
+    else scd::segment_sum_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(X, order, offsets, K, D, sums);
     SCD_LAUNCH_CHECK("segment_sum_kernel");
   } else if (N > 0) {
     dim3 grid((unsigned)K, (unsigned)((D + 127) / 128));
@@ -387,6 +403,7 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
   p.part_max = reinterpret_cast<float*>(w8 + pl.off_max);
   p.part_sum = reinterpret_cast<float*>(w8 + pl.off_sum);
   p.scratch = reinterpret_cast<float*>(w8 + pl.off_scratch);
+  p.prof = g_name_prof;
   if (pl.n_vsplit > 1) SCD_CUDA(cudaMemsetAsync(p.part_idx, 0xFF, pl.idx_bytes, st));   // -1: "row has nothing in this part"
 
   int e = 0;
@@ -397,7 +414,7 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
 
   const bool stats = want_softmax || row_max || row_sumexp;
   scd::topk_merge_kernel<int, false><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(
-      p.part_val, p.part_idx, stats ? p.part_max : nullptr, stats ? p.part_sum : nullptr, pl.n_vsplit, N, pl.kt, k, scale,
+      p.part_val, p.part_idx, stats ? p.part_max : nullptr, stats ? p.part_sum : nullptr, pl.n_vsplit * scd::kEpiHalves, N, pl.kt, k, scale,
       want_softmax ? 1 : 0, idx_offset, vals, reinterpret_cast<long long*>(idx), row_max, row_sumexp);
   SCD_LAUNCH_CHECK("topk_merge_kernel");
   return 0;

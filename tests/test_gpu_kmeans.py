@@ -49,7 +49,8 @@ def test_pairwise_distance_and_estep(n, d, k):
     kmeans._estep(X.cuda(), C.cuda(), labels, acc, mind)
     _assert_labels(labels, X, C)
     assert torch.allclose(mind.cpu(), ref.min(dim=1).values, atol=ATOL, rtol=0)
-    assert abs(acc.item() - ref.min(dim=1).values.double().sum().item()) < 1e-3
+    # inertia: mean per-row error below 1e-6 (the per-distance tolerance is 1e-4)
+    assert abs(acc.item() - ref.min(dim=1).values.double().sum().item()) < 1e-6 * max(n, 1000)
     assert torch.equal(kmeans.predict(X.cuda(), C.cuda()), labels)
     exact = torch.empty_like(labels)                                           # the fp32 direct-form E-step kernel
     kmeans._estep(X.cuda(), C.cuda(), exact, None, exact=True)

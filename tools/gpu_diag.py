@@ -136,6 +136,31 @@ def step_naming_time():
         print(f'{name} C2: {e0.elapsed_time(e1)/5:.3f} ms')
 
 
+def step_name_prof():
+    """Cycle counters of the naming kernel's issuer / epilogue (scd_debug_set_name_profile)."""
+    import torch
+    from scd_b200 import naming, _lib
+    n, v, d = 127000, 21000, 768
+    X = torch.randn(n, d, device='cuda'); X = (X / X.norm(dim=1, keepdim=True)).bfloat16()
+    W = torch.randn(v, d, device='cuda'); W = (W / W.norm(dim=1, keepdim=True)).bfloat16()
+    vocab = naming.Vocabulary.from_rows(W)
+    for _ in range(2):
+        naming.name_topk_raw(X, vocab, 5, False)
+    prof = torch.zeros(74, 16, dtype=torch.int64, device='cuda')
+    _lib.load().scd_debug_set_name_profile(prof.data_ptr())
+    naming.name_topk_raw(X, vocab, 5, False)
+    torch.cuda.synchronize()
+    _lib.load().scd_debug_set_name_profile(None)
+    p = prof.cpu().double()
+    names = {0: 'issuer total', 1: 'issuer wait tmem_empty', 2: 'issuer wait a_full', 3: 'issuer wait b_full (blocking)',
+             4: 'issuer b-not-ready events', 5: 'tiles', 8: 'epi total', 9: 'epi wait tmem_full', 10: 'epi item-final scan'}
+    for k, nm in names.items():
+        col = p[:, k]
+        print(f'{nm:32s} mean={col.mean():12.0f} min={col.min():12.0f} max={col.max():12.0f}')
+    print('issuer busy-issue cycles per tile:', float(((p[:, 0] - p[:, 1] - p[:, 2] - p[:, 3]) / p[:, 5]).mean()))
+    print('per-pair issuer total (first 10):', p[:10, 0].tolist())
+
+
 STEPS = ['kmeans', 'naming_tiny', 'naming_shapes', 'vote', 'naming_time']
 
 if __name__ == '__main__':
