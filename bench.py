@@ -156,60 +156,114 @@ def cpu_round_ms(cfg, sample_rows, threads, repeats=2):
 
 # ------------------------------------------------------------------------------------------ GPU arm
 class Round:
-    """Device-resident state of one rank and the launches of one naming round."""
+    """Device-resident state of one rank and the launches of one naming round.
 
-    def __init__(self, cfg, rank, world, group):
+    N = 1: everything local.  N > 1: image rows block-sharded over the ranks for BOTH contractions - k-means
+    (one packed NCCL all-reduce of [K*D sums | K counts | inertia] per iteration) and naming (every rank
+    holds the whole vocabulary, 32 MB, so its rows' top-k needs no exchange) - then the per-row results
+    (labels, top-k name indices; N*48 bytes in total) are all-gathered and the vote runs replicated.
+    `naming_shard='vocab'` switches naming to the vocabulary-column-sharded scheme (all rows x V/N columns per
+    rank, all-gather of [N, k] lists, k-way merge kernel)."""
+
+    def __init__(self, cfg, rank, world, group, naming_shard='rows'):
         from scd_b200 import dist as sdist, kmeans, naming, synth
         self.cfg, self.rank, self.world, self.group = cfg, rank, world, group
         self.kmeans, self.naming, self.sdist = kmeans, naming, sdist
+        self.naming_shard = naming_shard if world > 1 else 'rows'
         data = synth.make(cfg)
         self.host = data
         dev = torch.device('cuda')
         self.row_lo, self.row_hi = sdist.shard_bounds(cfg.n, world, rank)
-        self.col_lo, self.col_hi = sdist.shard_bounds(cfg.v, world, rank)
-        # resident operands: my row shard of X (fp32), all rows of Xc (bf16), my column shard of the vocabulary
+        n_local = self.row_hi - self.row_lo
         self.X = data['X'][self.row_lo:self.row_hi].to(dev).contiguous()
-        self.Xc = naming._feats_bf16(data['Xc'])
-        self.vocab = naming.Vocabulary(data['W'][:, self.col_lo:self.col_hi].to(dev), col_offset=self.col_lo)
         self.C = data['C0'].to(dev).contiguous()
         self.C_new = torch.empty_like(self.C)
-        n_local = self.X.shape[0]
-        self.labels = torch.empty(n_local, dtype=torch.int64, device=dev)
-        self.labels_all = torch.empty(cfg.n, dtype=torch.int64, device=dev) if world > 1 else self.labels
         self.inertia = torch.zeros(1, dtype=torch.float64, device=dev)
         self.mstep = kmeans._MStep(n_local, synth.D, cfg.k, dev)
         self.km = kmeans.K_Means(k=cfg.k, process_group=group if world > 1 else None)
+        if world > 1:
+            self.g_labels = sdist.RowGather(cfg.n, (), torch.int64, dev, group)
+            self.labels = self.g_labels.local
+        else:
+            self.g_labels = None
+            self.labels = torch.empty(n_local, dtype=torch.int64, device=dev)
+        if self.naming_shard == 'rows':
+            self.col_lo, self.col_hi = 0, cfg.v
+            self.Xc = naming._feats_bf16(data['Xc'][self.row_lo:self.row_hi])
+            self.vocab = naming.Vocabulary(data['W'].to(dev))
+            if world > 1:
+                self.g_idx = sdist.RowGather(cfg.n, (5,), torch.int64, dev, group)
+                self.topk = naming.TopKPlan(n_local, cfg.v, 5, dev, idx_out=self.g_idx.local)
+            else:
+                self.g_idx = None
+                self.topk = naming.TopKPlan(n_local, cfg.v, 5, dev)
+            self.name_flops = 2.0 * n_local * cfg.v * synth.D
+        else:
+            self.col_lo, self.col_hi = sdist.shard_bounds(cfg.v, world, rank)
+            self.Xc = naming._feats_bf16(data['Xc'])
+            self.vocab = naming.Vocabulary(data['W'][:, self.col_lo:self.col_hi].to(dev), col_offset=self.col_lo)
+            self.g_idx = None
+            self.topk = naming.TopKPlan(cfg.n, self.col_hi - self.col_lo, 5, dev, want_stats=True)
+            self.name_flops = 2.0 * cfg.n * (self.col_hi - self.col_lo) * synth.D
+        self.vote_plan = naming.VotePlan(cfg.n, cfg.k, 20, dev)
         self.launches_per_round = 0
-        self.ev_name = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        self.name_ms = []
+        self.ev_name = None
+        self.graph = None
 
-    def run(self, record_naming=False):
+    def run(self, ev_name=None):
         cfg, km, nm = self.cfg, self.kmeans, self.naming
         launches = 0
         # ---- k-means iteration: E-step, M-step sums, (all-reduce), divide + centre shift
         self.inertia.zero_()
-        km._estep(self.X, self.C, self.labels, self.inertia); launches += 1
-        self.mstep.sums_counts(self.X, self.labels); launches += 4
+        km._estep(self.X, self.C, self.labels, self.inertia); launches += 2           # centroid split + E-step
+        self.mstep.sums_counts(self.X, self.labels); launches += 4                    # hist, scan, scatter, segment sum
         counts_f = self.km._allreduce(self.mstep, self.inertia)
+        launches += 1 if counts_f is not None else 0                                  # pack (the all-reduce is NCCL's)
         self.mstep.finalize(self.C, self.C_new, counts_f); launches += 2
         # ---- full-vocabulary scoring + per-image top-5
-        if record_naming:
-            self.ev_name[0].record()
-        if self.world == 1:
-            vals, idx, _, _ = nm.name_topk_raw(self.Xc, self.vocab, 5, False); launches += 2
+        if ev_name is not None:
+            ev_name[0].record()
+        if self.naming_shard == 'rows':
+            vals, idx, _, _ = self.topk.run(self.Xc, self.vocab, False); launches += 2
         else:
-            vals, idx = self.sdist.sharded_score_topk(self.Xc, self.vocab, 5, False, self.group); launches += 3
-        if record_naming:
-            self.ev_name[1].record()
-        # ---- per-cluster vote (labels of all rows; replicated on every rank when sharded)
-        if self.world > 1:
-            import torch.distributed as dist
-            parts = [self.labels_all[lo:hi] for lo, hi in (self.sdist.shard_bounds(cfg.n, self.world, r) for r in range(self.world))]
-            dist.all_gather(parts, self.labels, group=self.group)
-        out = nm.vote_device(idx, self.labels_all, cfg.k, 5, 20); launches += 4
+            vals, idx = self.sdist.sharded_score_topk(self.Xc, self.vocab, 5, False, self.group, plan=self.topk); launches += 3
+        if ev_name is not None:
+            ev_name[1].record()
+        # ---- per-cluster vote over all rows
+        if self.world == 1:
+            out = nm.vote_device(idx, None, cfg.k, 5, 20, plan=self.vote_plan, presorted=self.mstep); launches += 1
+        else:
+            labels_all = self.g_labels.gather()
+            idx_all = self.g_idx.gather() if self.g_idx is not None else idx
+            out = nm.vote_device(idx_all, labels_all, cfg.k, 5, 20, plan=self.vote_plan); launches += 4
         self.launches_per_round = launches
         self.last = (vals, idx, out)
         return out
+
+    def capture(self):
+        """Record one round into a CUDA graph (launch-bound at N > 1: ~15 launches of 5-400 us each)."""
+        try:
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.run()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                self.run()
+            self.graph = g
+        except Exception as e:                                  # eager launches are always available
+            sys.stderr.write(f'[bench] CUDA graph capture failed, timing eager launches: {e}\n')
+            self.graph = None
+            torch.cuda.synchronize()
+        return self.graph is not None
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.run()
 
 
 def e2e_round(cfg, host, vocab, pinned):
@@ -237,6 +291,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default='C2')
+    ap.add_argument('--naming-shard', default='rows', choices=['rows', 'vocab'],
+                    help='N > 1: how the scoring/top-k is partitioned (rows: no exchange; vocab: all-gather + k-way merge)')
+    ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of CUDA-graph replays')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-clocks', action='store_true')
@@ -248,9 +305,18 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    feat_mb = cfg.n * synth.D * 6 / 1e6
+    voc_mb = cfg.v * synth.D * 2 / 1e6
+    if world == 1:
+        par = 'single GPU'
+    elif args.naming_shard == 'rows':
+        par = (f'rows/{world} for k-means (packed NCCL all-reduce of sums+counts+inertia) and for naming (vocabulary replicated, '
+               f'no exchange); labels + top-k indices all-gathered, vote replicated')
+    else:
+        par = f'rows/{world} (k-means, all-reduce) x vocab/{world} (naming, all-gather + k-way merge); vote replicated'
     config = dict(workload=f'{cfg.name}: {cfg.n}x{synth.D} image features, K={cfg.k}, V={cfg.v} names, top-5, vote top-20',
-                  n=cfg.n, d=synth.D, k=cfg.k, v=cfg.v, topk=5, l2='inputs (585 MB features + 32 MB vocabulary) exceed the 126 MB L2',
-                  parallelism=('single GPU' if world == 1 else f'rows/{world} (k-means, all-reduce) x vocab/{world} (naming, all-gather + merge)'))
+                  n=cfg.n, d=synth.D, k=cfg.k, v=cfg.v, topk=5,
+                  l2=f'inputs ({feat_mb:.0f} MB features + {voc_mb:.0f} MB vocabulary) exceed the 126 MB L2', parallelism=par)
 
     # -------------------------------------------------------------------------------- reference arm
     if args.impl == 'reference':
@@ -280,7 +346,7 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
         group = dist.group.WORLD
     peaks = load_peaks()
-    rnd = Round(cfg, rank, world, group)
+    rnd = Round(cfg, rank, world, group, args.naming_shard)
 
     def barrier():
         if world > 1:
@@ -291,20 +357,37 @@ def main():
     for _ in range(args.warmup):
         rnd.run()
     barrier()
+    graphed = False if args.no_graph else rnd.capture()
+    if world > 1:                                   # every rank must take the same path (collectives inside)
+        import torch.distributed as dist
+        flag = torch.tensor([1 if graphed else 0], device='cuda')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if not bool(flag.item()):
+            rnd.graph, graphed = None, False
+    if graphed:
+        for _ in range(2):
+            rnd.step()
+    barrier()
     sampler = ClockSampler(physical_gpu_index(local_rank), enabled=not args.no_clocks)
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    name_evs = []
     ev0.record()
     for _ in range(args.steps):
-        rnd.run(record_naming=True)
-        name_evs.append(rnd.ev_name)
-        rnd.ev_name = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        rnd.step()
     ev1.record()
     barrier()
     clocks = sampler.result()
     ms_total = ev0.elapsed_time(ev1)
+
+    # the dominant kernel, timed live with events around its launch (eager launches, same stream, same inputs)
+    n_k = max(3, min(args.steps, 20))
+    name_evs = []
+    for _ in range(n_k):
+        evs = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        rnd.run(ev_name=evs)
+        name_evs.append(evs)
+    barrier()
     name_ms = float(np.mean([a.elapsed_time(b) for a, b in name_evs]))
     t = torch.tensor([ms_total, name_ms], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -313,8 +396,8 @@ def main():
     ms_per_step = float(t[0]) / args.steps
     name_ms = float(t[1])
 
-    # roofline of the dominant kernel: fused scoring/top-k (tensor-core bound); algorithmic flops = 2*N*V*D / ranks
-    flops = 2.0 * cfg.n * (rnd.col_hi - rnd.col_lo) * synth.D
+    # roofline of the dominant kernel: fused scoring/top-k (tensor-core bound); algorithmic flops = 2 * rows * cols * D of this rank
+    flops = rnd.name_flops
     achieved = flops / (name_ms * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
@@ -323,8 +406,8 @@ def main():
             traffic = json.load(f).get('name_topk_kernel_dram_bytes_per_launch')
     roofline = dict(bound='tensor', kernel='name_topk_kernel<5> (+ topk_merge)', achieved=round(achieved, 1), peak=peaks['tflops'],
                     unit='TFLOP/s', frac=round(achieved / peaks['tflops'], 4), traffic=traffic,
-                    peak_source=f"{peaks['source']} bf16 burst (MEASURED_PEAKS.json)", kernel_ms=round(name_ms, 4),
-                    flops_per_launch=flops)
+                    peak_source=f"{peaks['source']} bf16 burst (MEASURED_PEAKS.json); sustained figure: {peaks['tflops_sustained']}",
+                    kernel_ms=round(name_ms, 4), flops_per_launch=flops)
 
     e2e = None
     cpu_baseline = None
@@ -352,12 +435,19 @@ def main():
         line = dict(metric=METRIC, value=round(ms_per_step, 4), unit='ms', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=round(ms_per_step, 4), higher_is_better=False, scaling='strong', vs_baseline=None, dtype='bf16',
                     data='synthetic', config=config, clocks=clocks, e2e=e2e, gpu_launches=rnd.launches_per_round * args.steps,
+                    launch_mode='cuda-graph replay' if graphed else 'eager',
                     roofline=roofline, cpu_baseline=cpu_baseline,
-                    split=dict(naming_ms=round(name_ms, 4), kmeans_vote_ms=round(ms_per_step - name_ms, 4)))
-        print(json.dumps(line))
+                    split=dict(naming_ms=round(name_ms, 4), rest_ms=round(ms_per_step - name_ms, 4)))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroy_process_group() / interpreter exit can block for minutes while
+        # a CUDA graph that captured NCCL kernels is still alive (seen on the 2-GPU box).  Every rank has passed
+        # the final barrier and rank 0 has flushed its line, so a hard exit loses nothing.
+        rnd.graph = None
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

@@ -73,6 +73,12 @@ SCD_API int scd_mstep_sums(const float* X, const int64_t* labels, int64_t N, int
 /* centers = sums / counts (empty cluster -> NaN row, like torch.mean over zero rows; no relocation), and
  * faster_mix_k_means_pytorch.py:71 / :123: *shift = sum_k ||C_new[k]-C_old[k]||_2 (C_old, shift nullable).
  * counts_f (nullable) takes float counts instead (e.g. after a packed fp32 all-reduce). ws: K floats. */
+/* Row-sharded k-means: tail of the packed fp32 all-reduce buffer [K*D sums | K counts | inertia]:
+ * out[0..K) = (float)counts, out[K] = (float)*inertia (0 when NULL).  The host layer all-reduces the buffer
+ * (NCCL) between scd_mstep_sums and scd_finalize_centers(counts_f = out). */
+SCD_API int scd_pack_counts_inertia(const int32_t* counts, const double* inertia /* nullable */, int K, float* out,
+                            scd_stream_t stream);
+
 SCD_API int scd_finalize_centers(const float* sums, const int32_t* counts, const float* counts_f, const float* C_old,
                          float* C_new, float* shift, int K, int D, void* ws, size_t ws_bytes, scd_stream_t stream);
 
@@ -114,6 +120,15 @@ SCD_API int scd_vote(const int64_t* topk_idx, int k_total, int k_used, const int
              const int64_t* excluded, int n_excluded, int M, int64_t* out_names, int32_t* out_counts,
              int32_t* out_distinct, int32_t* out_rows, int32_t* overflow, void* ws, size_t ws_bytes,
              scd_stream_t stream);
+
+/* Same vote when the rows were already sorted by these very cluster labels: `mstep_ws` is the workspace a
+ * scd_mstep_sums(X, labels, N, D, K, ...) call on the same labels has just filled (k-means labels are what
+ * main_unsup.py:575 votes with) - the counting sort is not repeated.  Per-cluster row counts are the
+ * M-step's `counts`. */
+SCD_API int scd_vote_presorted(const int64_t* topk_idx, int k_total, int k_used, const void* mstep_ws, int64_t N, int K,
+                       const int64_t* excluded /* nullable */, int n_excluded, int M,
+                       int64_t* out_names, int32_t* out_counts, int32_t* out_distinct, int32_t* overflow,
+                       scd_stream_t stream);
 
 /* ---------------------------------------------------------------- host-side combinatorial step (a10) */
 

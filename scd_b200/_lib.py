@@ -24,6 +24,7 @@ SIGNATURES = {
     'scd_labelled_inertia': (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp, _vp]),
     'scd_mstep_workspace_bytes': (_sz, [_i64, _int]),
     'scd_mstep_sums': (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _sz, _vp]),
+    'scd_pack_counts_inertia': (_int, [_vp, _vp, _int, _vp, _vp]),
     'scd_finalize_centers': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _vp]),
     'scd_vocab_prepare': (_int, [_vp, _int, _int, _i64, _i64, _vp, _vp]),
     'scd_cast_bf16': (_int, [_vp, _i64, _vp, _vp]),
@@ -33,6 +34,7 @@ SIGNATURES = {
     'scd_topk_merge': (_int, [_vp, _vp, _vp, _vp, _int, _i64, _int, _f32, _int, _vp, _vp, _vp]),
     'scd_vote_workspace_bytes': (_sz, [_i64, _int]),
     'scd_vote': (_int, [_vp, _int, _int, _vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'scd_vote_presorted': (_int, [_vp, _int, _int, _vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     'scd_linear_assignment': (_int, [_vp, _int, _int, _vp, C.POINTER(_int)]),
 }
 

@@ -314,6 +314,14 @@ __global__ void finalize_centers_kernel(const float* __restrict__ sums, const fl
   }
 }
 
+// tail of the packed all-reduce buffer [K*D sums | K counts | inertia], all fp32 (counts < 2^24 are exact)
+__global__ void pack_counts_inertia_kernel(const int* __restrict__ counts, const double* __restrict__ inertia, int K,
+                                           float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K) out[i] = (float)counts[i];
+  else if (i == K) out[K] = inertia ? (float)*inertia : 0.f;
+}
+
 // shift = sum_k move_norm[k], one block, fixed order (deterministic)
 __global__ void sum_small_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
   __shared__ float sh[1024];

@@ -308,6 +308,13 @@ int scd_mstep_sums(const float* X, const int64_t* labels, int64_t N, int D, int 
   return 0;
 }
 
+int scd_pack_counts_inertia(const int32_t* counts, const double* inertia, int K, float* out, scd_stream_t stream) {
+  if (K <= 0 || !counts || !out) return fail("scd_pack_counts_inertia: bad arguments");
+  scd::pack_counts_inertia_kernel<<<(K + 1 + 255) / 256, 256, 0, as_stream(stream)>>>(counts, inertia, K, out);
+  SCD_LAUNCH_CHECK("pack_counts_inertia_kernel");
+  return 0;
+}
+
 int scd_finalize_centers(const float* sums, const int32_t* counts, const float* counts_f, const float* C_old, float* C_new,
                          float* shift, int K, int D, void* ws, size_t ws_bytes, scd_stream_t stream) {
   if (K <= 0 || D <= 0) return fail("scd_finalize_centers: bad shape");
@@ -438,6 +445,22 @@ size_t scd_vote_workspace_bytes(int64_t N, int K) {
   return align_up((size_t)(3 * (size_t)K + 1 + (size_t)std::max<int64_t>(N, 0)) * sizeof(int), 256) + 256;
 }
 
+static int launch_vote(const int64_t* topk_idx, int k_total, int k_used, const int* order, const int* offsets, int K,
+                       const int64_t* excluded, int n_excluded, int M, int64_t* out_names, int32_t* out_counts,
+                       int32_t* out_distinct, int32_t* overflow, cudaStream_t st) {
+  SCD_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), st));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SCD_CUDA(cudaFuncSetAttribute(scd::vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scd::kVoteSmemBytes));
+    attr_set = true;
+  }
+  scd::vote_kernel<<<K, scd::kVoteThreads, scd::kVoteSmemBytes, st>>>(
+      reinterpret_cast<const long long*>(topk_idx), k_total, k_used, order, offsets, K, reinterpret_cast<const long long*>(excluded),
+      n_excluded, M, reinterpret_cast<long long*>(out_names), out_counts, out_distinct, overflow);
+  SCD_LAUNCH_CHECK("vote_kernel");
+  return 0;
+}
+
 int scd_vote(const int64_t* topk_idx, int k_total, int k_used, const int64_t* cluster_of_row, int64_t N, int K,
              const int64_t* excluded, int n_excluded, int M, int64_t* out_names, int32_t* out_counts, int32_t* out_distinct,
              int32_t* out_rows, int32_t* overflow, void* ws, size_t ws_bytes, scd_stream_t stream) {
@@ -454,17 +477,22 @@ int scd_vote(const int64_t* topk_idx, int k_total, int k_used, const int64_t* cl
   int* order = cursor + K;
   if (int e = sort_rows_by_label(cluster_of_row, N, K, counts, offsets, cursor, order, st)) return e;
   SCD_CUDA(cudaMemcpyAsync(out_rows, counts, sizeof(int) * (size_t)K, cudaMemcpyDeviceToDevice, st));
-  SCD_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), st));
-  static bool attr_set = false;
-  if (!attr_set) {
-    SCD_CUDA(cudaFuncSetAttribute(scd::vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scd::kVoteSmemBytes));
-    attr_set = true;
-  }
-  scd::vote_kernel<<<K, scd::kVoteThreads, scd::kVoteSmemBytes, st>>>(
-      reinterpret_cast<const long long*>(topk_idx), k_total, k_used, order, offsets, K, reinterpret_cast<const long long*>(excluded),
-      n_excluded, M, reinterpret_cast<long long*>(out_names), out_counts, out_distinct, overflow);
-  SCD_LAUNCH_CHECK("vote_kernel");
-  return 0;
+  return launch_vote(topk_idx, k_total, k_used, order, offsets, K, excluded, n_excluded, M, out_names, out_counts, out_distinct,
+                     overflow, st);
+}
+
+int scd_vote_presorted(const int64_t* topk_idx, int k_total, int k_used, const void* mstep_ws, int64_t N, int K,
+                       const int64_t* excluded, int n_excluded, int M, int64_t* out_names, int32_t* out_counts,
+                       int32_t* out_distinct, int32_t* overflow, scd_stream_t stream) {
+  if (N < 0 || K <= 0 || k_total <= 0 || k_used <= 0 || k_used > k_total || M <= 0) return fail("scd_vote_presorted: bad arguments");
+  if (N * (int64_t)k_used >= (1ll << 32)) return fail("scd_vote_presorted: N * k_used exceeds the 32-bit position range");
+  if (!topk_idx || !mstep_ws || !out_names || !out_counts || !out_distinct || !overflow) return fail("scd_vote_presorted: null pointer");
+  if (n_excluded > 0 && !excluded) return fail("scd_vote_presorted: excluded list is null");
+  // layout written by scd_mstep_sums: offsets[K+1] | cursor[K] | order[N]
+  const int* offsets = reinterpret_cast<const int*>(mstep_ws);
+  const int* order = offsets + 2 * K + 1;
+  return launch_vote(topk_idx, k_total, k_used, order, offsets, K, excluded, n_excluded, M, out_names, out_counts, out_distinct,
+                     overflow, as_stream(stream));
 }
 
 }  // extern "C"

@@ -18,7 +18,7 @@ namespace scd {
 
 constexpr int kVoteSlots = 16384;                       // power of two
 constexpr int kVoteThreads = 512;
-constexpr int kVoteSmemBytes = kVoteSlots * 12;         // keys + counts + first positions
+constexpr int kVoteSmemBytes = kVoteSlots * 14;         // keys + counts + first positions + live-slot list (u16)
 
 __global__ void __launch_bounds__(kVoteThreads)
 vote_kernel(const long long* __restrict__ topk_idx, int k_total, int k_used,
@@ -30,6 +30,8 @@ vote_kernel(const long long* __restrict__ topk_idx, int k_total, int k_used,
   int* keys = vote_sh;
   int* cnts = vote_sh + kVoteSlots;
   unsigned* firsts = reinterpret_cast<unsigned*>(vote_sh + 2 * kVoteSlots);
+  unsigned short* live = reinterpret_cast<unsigned short*>(vote_sh + 3 * kVoteSlots);   // slots in use, dense
+  __shared__ int n_live;
   __shared__ unsigned long long red[kVoteThreads / 32];
   __shared__ int red_slot[kVoteThreads / 32];
   __shared__ unsigned long long chosen_key;
@@ -38,7 +40,7 @@ vote_kernel(const long long* __restrict__ topk_idx, int k_total, int k_used,
 
   const int c = blockIdx.x;
   for (int s = threadIdx.x; s < kVoteSlots; s += blockDim.x) { keys[s] = -1; cnts[s] = 0; firsts[s] = 0xFFFFFFFFu; }
-  if (threadIdx.x == 0) n_distinct = 0;
+  if (threadIdx.x == 0) { n_distinct = 0; n_live = 0; }
   __syncthreads();
 
   const int p0 = offsets[c], p1 = offsets[c + 1];
@@ -64,15 +66,19 @@ vote_kernel(const long long* __restrict__ topk_idx, int k_total, int k_used,
     }
   }
   __syncthreads();
+  // dense list of the slots in use: the M selection rounds below scan n_distinct entries, not 16384 slots
+  for (int s = threadIdx.x; s < kVoteSlots; s += blockDim.x)
+    if (keys[s] >= 0) live[atomicAdd(&n_live, 1)] = (unsigned short)s;
   if (threadIdx.x == 0) { out_distinct[c] = n_distinct; chosen_key = ~0ull; }
   __syncthreads();
+  const int nl = n_live;
 
   // M rounds of "largest (count, earliest first) strictly below the previous pick"
   for (int m = 0; m < M; ++m) {
     const unsigned long long limit = chosen_key;
     unsigned long long best = 0ull; int best_slot = -1;
-    for (int s = threadIdx.x; s < kVoteSlots; s += blockDim.x) {
-      if (keys[s] < 0) continue;
+    for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+      const int s = live[i];
       const unsigned long long key = ((unsigned long long)(unsigned)cnts[s] << 32) | (unsigned long long)(0xFFFFFFFFu - firsts[s]);
       if (key < limit && (best_slot < 0 || key > best)) { best = key; best_slot = s; }
     }

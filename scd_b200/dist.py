@@ -19,46 +19,89 @@ def shard_bounds(total: int, world: int, rank: int):
     return lo, min(lo + per, total)
 
 
+def packed_slices(k: int, d: int):
+    """Layout of the packed fp32 M-step buffer ``[K*D sums | K counts | inertia]``."""
+    return slice(0, k * d), slice(k * d, k * d + k), slice(k * d + k, k * d + k + 1)
+
+
+def allreduce_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """The one exchange step of row-sharded k-means: sum the packed buffer over the ranks, in place."""
+    import torch.distributed as dist
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed
+
+
+class RowGather:
+    """All-gather of row-sharded per-row results (labels ``[n]``, top-k indices ``[n, k]``) into the full
+    ``[N, ...]`` tensor on every rank.  Shards are the ceil-sized blocks of ``shard_bounds``; the ragged last
+    block is padded to the common block size so a single ``all_gather_into_tensor`` does it."""
+
+    def __init__(self, n_total: int, tail_shape, dtype, device, group=None, fill=-1):
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n_total = int(n_total)
+        self.per = (self.n_total + self.world - 1) // self.world
+        self.lo, self.hi = shard_bounds(self.n_total, self.world, self.rank)
+        tail = tuple(tail_shape)
+        self.full_padded = torch.full((self.world * self.per,) + tail, fill, dtype=dtype, device=device)
+        self.local_padded = torch.full((self.per,) + tail, fill, dtype=dtype, device=device)
+        self.local = self.local_padded[:self.hi - self.lo]      # kernels write this rank's results here
+        self.full = self.full_padded[:self.n_total]
+
+    def gather(self):
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(self.full_padded, self.local_padded, group=self.group)
+        return self.full
+
+
+def merge_topk_stacked(vals, idx, pmax, psum, k: int, softmax: bool, scale: float = 100.0):
+    """vals / idx ``[parts, N, k]`` (scaled logits, global int64 indices) and, for the softmax, per-part
+    ``row_max / row_sumexp [parts, N]`` -> merged ``(vals [N,k], idx [N,k])`` (probabilities when ``softmax``)."""
+    from . import _lib
+    lib = _lib.load()
+    parts, n = int(vals.shape[0]), int(vals.shape[1])
+    out_v = torch.empty(n, k, dtype=torch.float32, device=vals.device)
+    out_i = torch.empty(n, k, dtype=torch.int64, device=vals.device)
+    _lib.check(lib.scd_topk_merge(vals.data_ptr(), idx.data_ptr(), _lib.ptr(pmax) if softmax else None,
+                                  _lib.ptr(psum) if softmax else None, parts, n, k, float(scale), int(bool(softmax)),
+                                  out_v.data_ptr(), out_i.data_ptr(), torch.cuda.current_stream().cuda_stream), 'scd_topk_merge')
+    return out_v, out_i
+
+
 def merge_topk_parts(parts, k: int, softmax: bool, scale: float = 100.0):
     """parts: list of ``(vals [N,k] scaled logits, idx [N,k] int64 global, row_max [N], row_sumexp [N])`` from
     ``naming.name_topk_raw(..., softmax=False, want_stats=True)`` on each vocabulary shard -> merged
     ``(vals, idx)`` (softmax probabilities when ``softmax``)."""
-    from . import _lib
-    lib = _lib.load()
     vals = torch.stack([p[0] for p in parts]).contiguous()
     idx = torch.stack([p[1] for p in parts]).contiguous()
-    n = int(vals.shape[1])
-    out_v = torch.empty(n, k, dtype=torch.float32, device=vals.device)
-    out_i = torch.empty(n, k, dtype=torch.int64, device=vals.device)
     pmax = psum = None
     if softmax:
         pmax = torch.stack([p[2] for p in parts]).contiguous()
         psum = torch.stack([p[3] for p in parts]).contiguous()
-    _lib.check(lib.scd_topk_merge(vals.data_ptr(), idx.data_ptr(), _lib.ptr(pmax), _lib.ptr(psum), len(parts), n, k,
-                                  float(scale), int(bool(softmax)), out_v.data_ptr(), out_i.data_ptr(),
-                                  torch.cuda.current_stream().cuda_stream), 'scd_topk_merge')
-    return out_v, out_i
+    return merge_topk_stacked(vals, idx, pmax, psum, k, softmax, scale)
 
 
-def sharded_score_topk(feats_bf16: torch.Tensor, vocab_shard, k: int, softmax: bool, group=None, scale: float = 100.0):
+def sharded_score_topk(feats_bf16: torch.Tensor, vocab_shard, k: int, softmax: bool, group=None, scale: float = 100.0,
+                       plan=None):
     """Vocabulary-column-parallel scoring: every rank holds all rows and its own ``naming.Vocabulary`` shard
     (``col_offset`` = first global column).  Local fused top-k -> all-gather -> k-way merge; every rank
     returns the full ``(vals [N,k], idx [N,k])``."""
     import torch.distributed as dist
     from . import naming
-    vals, idx, rmax, rsum = naming.name_topk_raw(feats_bf16, vocab_shard, k, False, scale, want_stats=True)
+    vals, idx, rmax, rsum = naming.name_topk_raw(feats_bf16, vocab_shard, k, False, scale, want_stats=True, plan=plan)
     world = dist.get_world_size(group)
     if world == 1:
-        return merge_topk_parts([(vals, idx, rmax, rsum)], k, softmax, scale)
-    gv = [torch.empty_like(vals) for _ in range(world)]
-    gi = [torch.empty_like(idx) for _ in range(world)]
-    dist.all_gather(gv, vals, group=group)
-    dist.all_gather(gi, idx, group=group)
+        return merge_topk_stacked(vals.unsqueeze(0), idx.unsqueeze(0), rmax.unsqueeze(0), rsum.unsqueeze(0), k, softmax, scale)
+    gv = torch.empty((world,) + tuple(vals.shape), dtype=vals.dtype, device=vals.device)
+    gi = torch.empty((world,) + tuple(idx.shape), dtype=idx.dtype, device=idx.device)
+    dist.all_gather_into_tensor(gv, vals, group=group)
+    dist.all_gather_into_tensor(gi, idx, group=group)
+    gm = gs = None
     if softmax:
-        gm = [torch.empty_like(rmax) for _ in range(world)]
-        gs = [torch.empty_like(rsum) for _ in range(world)]
-        dist.all_gather(gm, rmax, group=group)
-        dist.all_gather(gs, rsum, group=group)
-    else:
-        gm = gs = [None] * world
-    return merge_topk_parts(list(zip(gv, gi, gm, gs)), k, softmax, scale)
+        gm = torch.empty((world,) + tuple(rmax.shape), dtype=rmax.dtype, device=rmax.device)
+        gs = torch.empty((world,) + tuple(rsum.shape), dtype=rsum.dtype, device=rsum.device)
+        dist.all_gather_into_tensor(gm, rmax, group=group)
+        dist.all_gather_into_tensor(gs, rsum, group=group)
+    return merge_topk_stacked(gv, gi, gm, gs, k, softmax, scale)

@@ -57,7 +57,10 @@ class _MStep:
         lib = _lib.load()
         self.n, self.d, self.k = n, d, k
         self.ws = torch.empty(lib.scd_mstep_workspace_bytes(n, k), dtype=torch.uint8, device=device)
-        self.sums = torch.empty(k, d, dtype=torch.float32, device=device)
+        # one buffer [K*D sums | K counts | inertia] (fp32) so the row-sharded case all-reduces it in one call
+        self.packed = torch.zeros(k * d + k + 1, dtype=torch.float32, device=device)
+        self.sums = self.packed[:k * d].view(k, d)
+        self.counts_f = self.packed[k * d:k * d + k]
         self.counts = torch.empty(k, dtype=torch.int32, device=device)
         self.norm_ws = torch.empty(max(k, 1), dtype=torch.float32, device=device)
         self.shift = torch.zeros(1, dtype=torch.float32, device=device)
@@ -140,13 +143,13 @@ class K_Means:
         """one packed all-reduce of [K*D sums | K counts | inertia] when rows are sharded."""
         if self.process_group is None:
             return None
-        import torch.distributed as dist
-        packed = torch.cat((mstep.sums.view(-1).double(), mstep.counts.double(), inertia_acc.view(-1)))
-        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.process_group)
-        kd = mstep.k * mstep.d
-        mstep.sums.copy_(packed[:kd].view(mstep.k, mstep.d).float())
-        inertia_acc.copy_(packed[kd + mstep.k:])
-        return packed[kd:kd + mstep.k].float().contiguous()
+        from . import dist as sdist
+        lib = _lib.load()
+        _lib.check(lib.scd_pack_counts_inertia(mstep.counts.data_ptr(), inertia_acc.data_ptr(), mstep.k,
+                                               mstep.counts_f.data_ptr(), _stream()), 'scd_pack_counts_inertia')
+        sdist.allreduce_packed(mstep.packed, self.process_group)
+        inertia_acc.copy_(mstep.packed[-1:])
+        return mstep.counts_f
 
     def _lloyd(self, X_assign, X_all, labels, l_num, centers, l_feats=None):
         """The iteration loop shared by fit_once (:56-74) and fit_mix_once (:102-126).

@@ -100,25 +100,43 @@ def _as_vocab(w) -> Vocabulary:
     return w if isinstance(w, Vocabulary) else Vocabulary(w)
 
 
+class TopKPlan:
+    """Outputs + workspace of the fused scoring/top-k launch for fixed ``(n, V, k)``: a hot loop (or a CUDA
+    graph) re-launches without touching the allocator."""
+
+    def __init__(self, n: int, v: int, k: int, device, want_stats: bool = False, idx_out: torch.Tensor | None = None):
+        lib = _lib.load()
+        self.n, self.v, self.k = int(n), int(v), int(k)
+        self.vals = torch.empty(self.n, self.k, dtype=torch.float32, device=device)
+        if idx_out is not None:            # write the indices straight into a caller-owned [n, k] int64 buffer
+            assert idx_out.shape == (self.n, self.k) and idx_out.dtype == torch.int64 and idx_out.is_contiguous()
+        self.idx = idx_out if idx_out is not None else torch.empty(self.n, self.k, dtype=torch.int64, device=device)
+        self.rmax = torch.empty(self.n, dtype=torch.float32, device=device) if want_stats else None
+        self.rsum = torch.empty(self.n, dtype=torch.float32, device=device) if want_stats else None
+        self.ws = torch.empty(lib.scd_name_topk_workspace_bytes(self.n, self.v, self.k) if self.n else 256,
+                              dtype=torch.uint8, device=device)
+
+    def run(self, feats_bf16: torch.Tensor, vocab: 'Vocabulary', softmax: bool, scale: float = SCALE):
+        if int(feats_bf16.shape[0]) != self.n or vocab.V != self.v:
+            raise ValueError('TopKPlan was built for a different shape')
+        if self.n == 0:
+            return self.vals, self.idx, self.rmax, self.rsum
+        if int(feats_bf16.shape[1]) != vocab.D:
+            raise ValueError(f'feature width {int(feats_bf16.shape[1])} != vocabulary width {vocab.D}')
+        lib = _lib.load()
+        _lib.check(lib.scd_name_topk(feats_bf16.data_ptr(), self.n, vocab.D, vocab.Wt.data_ptr(), vocab.V, float(scale), self.k,
+                                     int(bool(softmax)), vocab.col_offset, self.vals.data_ptr(), self.idx.data_ptr(),
+                                     _lib.ptr(self.rmax), _lib.ptr(self.rsum), self.ws.data_ptr(), self.ws.numel(), _stream()),
+                   'scd_name_topk')
+        return self.vals, self.idx, self.rmax, self.rsum
+
+
 def name_topk_raw(feats_bf16: torch.Tensor, vocab: Vocabulary, k: int, softmax: bool, scale: float = SCALE,
-                  want_stats: bool = False):
+                  want_stats: bool = False, plan: TopKPlan | None = None):
     """One launch of the fused scoring/top-k kernel on device-resident operands."""
-    n = int(feats_bf16.shape[0])
-    dev = feats_bf16.device
-    vals = torch.empty(n, k, dtype=torch.float32, device=dev)
-    idx = torch.empty(n, k, dtype=torch.int64, device=dev)
-    rmax = torch.empty(n, dtype=torch.float32, device=dev) if want_stats else None
-    rsum = torch.empty(n, dtype=torch.float32, device=dev) if want_stats else None
-    if n == 0:
-        return vals, idx, rmax, rsum
-    if int(feats_bf16.shape[1]) != vocab.D:
-        raise ValueError(f'feature width {int(feats_bf16.shape[1])} != vocabulary width {vocab.D}')
-    lib = _lib.load()
-    ws = torch.empty(lib.scd_name_topk_workspace_bytes(n, vocab.V, k), dtype=torch.uint8, device=dev)
-    _lib.check(lib.scd_name_topk(feats_bf16.data_ptr(), n, vocab.D, vocab.Wt.data_ptr(), vocab.V, float(scale), int(k),
-                                 int(bool(softmax)), vocab.col_offset, vals.data_ptr(), idx.data_ptr(),
-                                 _lib.ptr(rmax), _lib.ptr(rsum), ws.data_ptr(), ws.numel(), _stream()), 'scd_name_topk')
-    return vals, idx, rmax, rsum
+    if plan is None:
+        plan = TopKPlan(int(feats_bf16.shape[0]), vocab.V, k, feats_bf16.device, want_stats)
+    return plan.run(feats_bf16, vocab, softmax, scale)
 
 
 def score_topk(feats, zeroshot_weights, k: int = 5, softmax: bool = False, scale: float = SCALE):
@@ -156,32 +174,59 @@ def reassign(feats, zeroshot_weights, cand_name_idx) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------------------- voting
+class VotePlan:
+    """Outputs + workspace of the device vote for fixed ``(n, K, M)``."""
+
+    def __init__(self, n: int, n_clusters: int, num_common: int, device):
+        lib = _lib.load()
+        self.n, self.K, self.M = int(n), int(n_clusters), int(num_common)
+        self.names = torch.empty(self.K, self.M, dtype=torch.int64, device=device)
+        self.counts = torch.empty(self.K, self.M, dtype=torch.int32, device=device)
+        self.distinct = torch.empty(self.K, dtype=torch.int32, device=device)
+        self.rows = torch.empty(self.K, dtype=torch.int32, device=device)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+        self.ws = torch.empty(lib.scd_vote_workspace_bytes(self.n, self.K), dtype=torch.uint8, device=device)
+
+
 def vote_device(name_idx_topk: torch.Tensor, cluster_of_row, n_clusters: int, top_k: int, num_common: int,
-                known_name_idx=None):
+                known_name_idx=None, plan: VotePlan | None = None, presorted=None):
     """Device vote: per cluster the ``num_common`` most common names of ``name_idx_topk[rows, :top_k]``
     (Python ``Counter.most_common`` order).  Returns device tensors
-    ``(names [K,M] int64 (-1 padded), counts [K,M] int32, distinct [K] int32, rows [K] int32)``."""
+    ``(names [K,M] int64 (-1 padded), counts [K,M] int32, distinct [K] int32, rows [K] int32, overflow [1])``.
+
+    ``presorted``: a ``kmeans._MStep`` whose ``sums_counts(X, labels)`` has just run on these very labels (the
+    k-means labels are what ``main_unsup.py:575`` votes with) - its label sort is reused instead of repeated."""
     _require_cuda()
-    idx = name_idx_topk.to('cuda').to(torch.int64).contiguous()
-    cl = torch.as_tensor(cluster_of_row).to('cuda').to(torch.int64).contiguous()
+    idx = name_idx_topk
+    if not (torch.is_tensor(idx) and idx.is_cuda and idx.dtype == torch.int64 and idx.is_contiguous()):
+        idx = torch.as_tensor(idx).to('cuda').to(torch.int64).contiguous()
     n, kt = int(idx.shape[0]), int(idx.shape[1])
     dev = idx.device
     K, M = int(n_clusters), int(num_common)
-    names = torch.empty(K, M, dtype=torch.int64, device=dev)
-    counts = torch.empty(K, M, dtype=torch.int32, device=dev)
-    distinct = torch.empty(K, dtype=torch.int32, device=dev)
-    rows = torch.empty(K, dtype=torch.int32, device=dev)
-    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    if plan is None:
+        plan = VotePlan(n, K, M, dev)
+    elif (plan.n, plan.K, plan.M) != (n, K, M):
+        raise ValueError('VotePlan was built for a different shape')
     excl = None
     if known_name_idx is not None and len(known_name_idx):
         excl = torch.as_tensor(np.asarray(list(known_name_idx), dtype=np.int64), device=dev)
     lib = _lib.load()
-    ws = torch.empty(lib.scd_vote_workspace_bytes(n, K), dtype=torch.uint8, device=dev)
+    if presorted is not None:
+        if (presorted.n, presorted.k) != (n, K):
+            raise ValueError('presorted M-step does not match the vote shape')
+        _lib.check(lib.scd_vote_presorted(idx.data_ptr(), kt, int(top_k), presorted.ws.data_ptr(), n, K, _lib.ptr(excl),
+                                          0 if excl is None else int(excl.numel()), M, plan.names.data_ptr(),
+                                          plan.counts.data_ptr(), plan.distinct.data_ptr(), plan.overflow.data_ptr(),
+                                          _stream()), 'scd_vote_presorted')
+        return plan.names, plan.counts, plan.distinct, presorted.counts, plan.overflow
+    cl = cluster_of_row
+    if not (torch.is_tensor(cl) and cl.is_cuda and cl.dtype == torch.int64 and cl.is_contiguous()):
+        cl = torch.as_tensor(cl).to('cuda').to(torch.int64).contiguous()
     _lib.check(lib.scd_vote(idx.data_ptr(), kt, int(top_k), cl.data_ptr(), n, K, _lib.ptr(excl),
-                            0 if excl is None else int(excl.numel()), M, names.data_ptr(), counts.data_ptr(),
-                            distinct.data_ptr(), rows.data_ptr(), overflow.data_ptr(), ws.data_ptr(), ws.numel(),
-                            _stream()), 'scd_vote')
-    return names, counts, distinct, rows, overflow
+                            0 if excl is None else int(excl.numel()), M, plan.names.data_ptr(), plan.counts.data_ptr(),
+                            plan.distinct.data_ptr(), plan.rows.data_ptr(), plan.overflow.data_ptr(), plan.ws.data_ptr(),
+                            plan.ws.numel(), _stream()), 'scd_vote')
+    return plan.names, plan.counts, plan.distinct, plan.rows, plan.overflow
 
 
 def vote(name_idx_topk, u_preds, cluster_ids, top_k: int, num_common: int, known_name_idx=None):

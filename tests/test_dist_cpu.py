@@ -3,7 +3,6 @@
 vocabulary-sharded top-k (the merge itself is a CUDA kernel, covered by the GPU tests)."""
 import os
 import socket
-import types
 
 import pytest
 import torch
@@ -34,32 +33,38 @@ def _worker(rank, world, port, k, d):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
-        from scd_b200 import kmeans
         g = torch.Generator().manual_seed(0)
         n = 101
         X = torch.randn(n, d, generator=g)
         labels = torch.randint(0, k, (n,), generator=g)
         lo, hi = sdist.shard_bounds(n, world, rank)
-        # what the M-step kernel would have produced on this rank's row shard
-        ms = types.SimpleNamespace(k=k, d=d, sums=torch.zeros(k, d), counts=torch.zeros(k, dtype=torch.int32))
-        ms.sums.index_add_(0, labels[lo:hi], X[lo:hi])
-        ms.counts += torch.bincount(labels[lo:hi], minlength=k).int()
-        inertia = torch.tensor([float(rank + 1)], dtype=torch.float64)
-        km = kmeans.K_Means(k=k, process_group=dist.group.WORLD)
-        counts_f = km._allreduce(ms, inertia)
+        # what the M-step kernels (scd_mstep_sums + scd_pack_counts_inertia) leave on this rank's row shard
+        s_sums, s_counts, s_inertia = sdist.packed_slices(k, d)
+        packed = torch.zeros(k * d + k + 1)
+        packed[s_sums].view(k, d).index_add_(0, labels[lo:hi], X[lo:hi])
+        packed[s_counts] = torch.bincount(labels[lo:hi], minlength=k).float()
+        packed[s_inertia] = float(rank + 1)
+        sdist.allreduce_packed(packed, dist.group.WORLD)
         want = torch.zeros(k, d).index_add_(0, labels, X)
-        assert torch.allclose(ms.sums, want, atol=1e-5)
-        assert torch.equal(counts_f.long(), torch.bincount(labels, minlength=k))
-        assert inertia.item() == sum(range(1, world + 1))
+        assert torch.allclose(packed[s_sums].view(k, d), want, atol=1e-5)
+        assert torch.equal(packed[s_counts].long(), torch.bincount(labels, minlength=k))
+        assert packed[s_inertia].item() == sum(range(1, world + 1))
         # all-gather plumbing used by sharded_score_topk: every rank ends with every shard's list, in rank order
         mine = torch.full((4, 5), float(rank))
         got = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(got, mine)
         assert [float(t[0, 0]) for t in got] == [float(r) for r in range(world)]
+        # row-sharded results (labels, top-k indices) gathered into the full [N, ...] tensor, ragged last shard
+        for tail, dtype in (((), torch.int64), ((5,), torch.int64)):
+            rg = sdist.RowGather(n, tail, dtype, 'cpu', dist.group.WORLD)
+            assert (rg.lo, rg.hi) == (lo, hi)
+            ref = torch.arange(n * max(1, int(torch.tensor(tail).prod()) if tail else 1)).view((n,) + tail)
+            rg.local.copy_(ref[lo:hi])
+            assert torch.equal(rg.gather(), ref)
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(120)
-def test_packed_allreduce_world2_gloo():
+def test_packed_allreduce_and_row_gather_world2_gloo():
     mp.spawn(_worker, args=(2, _free_port(), 6, 16), nprocs=2, join=True)
