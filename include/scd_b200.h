@@ -130,6 +130,24 @@ SCD_API int scd_vote_presorted(const int64_t* topk_idx, int k_total, int k_used,
                        int64_t* out_names, int32_t* out_counts, int32_t* out_distinct, int32_t* overflow,
                        scd_stream_t stream);
 
+/* ---------------------------------------------------------------- size-constrained assignment (a7) */
+
+/* counts[k] = |{i : labels[i] == k}| (int32 [K], overwritten); labels outside [0,K) are ignored.  The size check of
+ * the constrained E-step (is the plain argmin already within size_min..size_max?) and a building block of the M-step. */
+SCD_API int scd_label_histogram(const int64_t* labels, int64_t N, int K, int32_t* counts, scd_stream_t stream);
+
+
+/* local_utils/sskm_constrained.py:226-274 _labels_constrained (graph :277-328, OR-Tools solve :331-356):
+ * minimise sum_i cost[i, labels[i]] with size_min <= |cluster k| <= size_max for every k.
+ * cost: HOST int32 [N,K] = round(1000*sqrt(dist)) (scd_pairwise_distance's cost_x1000, copied to the host as the
+ * reference does, :116); labels: HOST int32 [N] (the reference's labels.astype(np.int32), :265).
+ * Exact optimum by successive shortest augmenting paths from the row-argmin assignment; *total_cost (nullable) is
+ * the optimal objective, *n_augment (nullable) the number of unit augmentations (0 = the bounds were inactive).
+ * Returns 0, 1 (bad arguments) or 2 (infeasible: the reference raises 'There was an issue with the min cost flow
+ * input.', :349-350).  Host-only: no stream, no device memory. */
+SCD_API int scd_constrained_assign(const int32_t* cost, int64_t N, int K, int64_t size_min, int64_t size_max,
+                           int32_t* labels, int64_t* total_cost /* nullable */, int64_t* n_augment /* nullable */);
+
 /* ---------------------------------------------------------------- host-side combinatorial step (a10) */
 
 /* gcd/project_utils/cluster_utils.py:234-275 linear_assignment (called from local_utils/clip_lang_util.py:178):

@@ -154,6 +154,59 @@ def gen_kmeans(km_local, km_gcd):
                         inertia=np.float64(km.inertia_.item()))
 
 
+# ------------------------------------------------------------------ constrained k-means fixtures
+def gen_constrained(ref):
+    """Runs the REAL ``local_utils/sskm_constrained.py`` (graph construction, ``_labels_constrained``, ``fit`` /
+    ``fit_mix``).  Its only missing dependency, the OR-Tools wrapper module
+    ``k_means_constrained.mincostflow_vectorized`` (requirements.txt:103, not installed), is replaced by
+    ``oracle.constrained_oracle.StandInMinCostFlow`` - so the solver is the stand-in, everything around it is the
+    reference itself (parity unpinned for the solver, see the oracle's header)."""
+    import importlib
+    from oracle import constrained_oracle as co
+    _stub('k_means_constrained')
+    _stub('k_means_constrained.mincostflow_vectorized', SimpleMinCostFlowVectorized=co.StandInMinCostFlow)
+    _stub('pyximport', install=lambda *a, **k: None)
+    sk = importlib.import_module('local_utils.sskm_constrained')
+    out = {}
+    # (1) the 9 x 2 array of local_utils/test_kmeans_cons.py:3 with its parameters (k=2, size 2..5, random_state=0)
+    X9 = torch.from_numpy(np.array([[1, 2], [1, 4], [1, 0], [4, 2], [4, 4], [4, 0], [4, 3], [4, 4], [4, 1]])).float()
+    km = sk.K_Means(k=2, size_min=2, size_max=5, random_state=0)
+    km.fit(X9)
+    out['t9_X'] = X9.numpy()
+    out['t9_labels'] = km.labels_.numpy()
+    out['t9_centers'] = km.cluster_centers_.numpy()
+    out['t9_inertia'] = np.float64(km.inertia_)
+    out['t9_n_iter'] = np.int64(km.n_iter_)
+    # (2) graph arrays + one constrained assignment on unit-norm features with ACTIVE bounds
+    n, d, k = 240, 32, 6
+    X, y = clustered_feats(n, d, k, seed=31)
+    C0 = X[:k].clone()
+    D_sqrt = torch.sqrt(sk.pairwise_distance(X, C0, None)).numpy()
+    lo, hi = 36, 44
+    edges, costs, caps, supplies, n_C, n_X = sk.minimum_cost_flow_problem_graph(X.numpy(), C0.numpy(), D_sqrt, lo, hi)
+    labels, inertia = sk._labels_constrained(X.numpy(), C0.numpy(), D_sqrt, size_min=lo, size_max=hi,
+                                             distances=np.zeros(n, dtype=np.float32))
+    out.update(g_X=X.numpy(), g_C0=C0.numpy(), g_D_sqrt=D_sqrt, g_bounds=np.array([lo, hi]), g_edges=edges, g_costs=costs,
+               g_caps=caps, g_supplies=supplies, g_labels=labels, g_inertia=np.float64(inertia),
+               g_total_cost=np.int64(costs[:n * k].reshape(n, k)[np.arange(n), labels].sum()))
+    # (3) whole fits: unsupervised (random init) and semi-supervised (k-means++ from the labelled means)
+    km = sk.K_Means(k=k, tolerance=1e-4, max_iterations=5, size_min=lo, size_max=hi, init='random', n_init=2, random_state=4,
+                    n_jobs=None, pairwise_batch_size=64)
+    km.fit(X)
+    out.update(fit_labels=km.labels_.numpy(), fit_centers=km.cluster_centers_.numpy(), fit_inertia=np.float64(km.inertia_),
+               fit_n_iter=np.int64(km.n_iter_))
+    lab = (y < k // 2) & (torch.rand(n, generator=torch.Generator().manual_seed(32)) < 0.5)
+    l_f, u_f, l_t = X[lab].contiguous(), X[~lab].contiguous(), y[lab].double()
+    lo_u, hi_u = 28, 36                               # bounds apply to the unlabelled rows only (:116)
+    km = sk.K_Means(k=k, tolerance=1e-4, max_iterations=5, size_min=lo_u, size_max=hi_u, init='k-means++', n_init=2,
+                    random_state=9, n_jobs=None, pairwise_batch_size=64)
+    km.fit_mix(u_f, l_f, l_t)
+    out.update(mix_u=u_f.numpy(), mix_l=l_f.numpy(), mix_t=l_t.numpy(), mix_bounds=np.array([lo_u, hi_u]),
+               mix_labels=km.labels_.numpy(), mix_centers=km.cluster_centers_.numpy(),
+               mix_inertia=np.float64(km.inertia_.item()), mix_n_iter=np.int64(km.n_iter_))
+    np.savez_compressed(os.path.join(OUT, 'kmeans_constrained.npz'), **out)
+
+
 # ------------------------------------------------------------------ Hungarian fixtures
 def gen_hungarian(cu):
     rng = np.random.RandomState(0)
@@ -297,6 +350,7 @@ def main():
     torch.set_num_threads(1)          # fixtures must not depend on the thread count of this box
     km_local, km_gcd, lang, cu = import_reference(a.ref)
     gen_kmeans(km_local, km_gcd)
+    gen_constrained(a.ref)
     gen_hungarian(cu)
     gen_naming(a.ref, lang)
     for f in sorted(os.listdir(OUT)):

@@ -277,6 +277,20 @@ static int sort_rows_by_label(const int64_t* labels, int64_t N, int K, int32_t* 
   return 0;
 }
 
+int scd_label_histogram(const int64_t* labels, int64_t N, int K, int32_t* counts, scd_stream_t stream) {
+  if (N < 0 || K <= 0) return fail("scd_label_histogram: bad shape N=%lld K=%d", (long long)N, K);
+  if (K * sizeof(int) > 48 * 1024) return fail("scd_label_histogram: K=%d too large for the shared-memory histogram", K);
+  if (!counts || (N > 0 && !labels)) return fail("scd_label_histogram: null pointer");
+  cudaStream_t st = as_stream(stream);
+  SCD_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)K, st));
+  if (N > 0) {
+    const int blocks = (int)std::min<long long>((N + 255) / 256, 148 * 8);
+    scd::label_hist_kernel<<<blocks, 256, sizeof(int) * (size_t)K, st>>>(reinterpret_cast<const long long*>(labels), N, K, counts);
+    SCD_LAUNCH_CHECK("label_hist_kernel");
+  }
+  return 0;
+}
+
 int scd_mstep_sums(const float* X, const int64_t* labels, int64_t N, int D, int K, float* sums, int32_t* counts, void* ws,
                    size_t ws_bytes, scd_stream_t stream) {
   if (N < 0 || D <= 0 || K <= 0) return fail("scd_mstep_sums: bad shape N=%lld D=%d K=%d", (long long)N, D, K);

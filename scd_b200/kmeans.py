@@ -151,6 +151,11 @@ class K_Means:
         inertia_acc.copy_(mstep.packed[-1:])
         return mstep.counts_f
 
+    def _assign(self, X, centers, labels_out, inertia_acc):
+        """E-step of one iteration: ``labels_out[i] = argmin_k ||X_i - c_k||^2`` and ``inertia_acc += sum of the
+        minima``.  (The size-constrained subclass overrides this with the min-cost-flow assignment.)"""
+        _estep(X, centers, labels_out, inertia_acc)
+
     def _lloyd(self, X_assign, X_all, labels, l_num, centers, l_feats=None):
         """The iteration loop shared by fit_once (:56-74) and fit_mix_once (:102-126).
 
@@ -170,7 +175,7 @@ class K_Means:
             n_done = it + 1
             inertia_acc.zero_()
             if X_assign.shape[0]:
-                _estep(X_assign, c_cur, u_view, inertia_acc)                       # :58-60 / :105-107,:111
+                self._assign(X_assign, c_cur, u_view, inertia_acc)                 # :58-60 / :105-107,:111
             if l_num:
                 lib = _lib.load()
                 _lib.check(lib.scd_labelled_inertia(l_feats.data_ptr(), labels.data_ptr(), l_num, d, c_cur.data_ptr(), k,
