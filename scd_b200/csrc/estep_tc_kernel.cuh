@@ -18,8 +18,9 @@
 // HBM-bound while 3 * K <~ 500 (K = 100 / 120 / 200); tensor-bound for K = 1000.
 //
 // Warp roles (512 threads, 1 CTA / SM, persistent over 128-row tiles):
-//   0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle | 4-11 converters (two sets of four warps
-//   that take alternate k-blocks, so every scheduler has two conversions in flight) | 12-15 epilogue
+//   0, 3 X TMA producers (alternate k-blocks) | 1 MMA issuer | 2 TMEM allocator, then centroid TMA producer (hi + lo
+//   planes as one 3-D box) | 4-11 converters (two sets of four warps that take alternate k-blocks, so every scheduler
+//   has two conversions in flight) | 12-15 epilogue
 #pragma once
 #include "ptx.cuh"
 #include <cuda_bf16.h>
@@ -64,11 +65,12 @@ struct EsParams {
   int num_kb;              // ceil(D / 32)
   int n_row_tiles;
   int x_stages;            // depth of the fp32 X ring (2 .. kEsMaxXStages)
-  int b_plane;             // bytes of one centroid plane stage: align_up(n_tile * 64, 1024)
+  int b_plane;             // bytes of one centroid plane stage: n_tile * 64 (n_tile % 16 == 0, so a multiple of 1024)
   const float* cnorm;      // [K]
   long long* labels;       // [N]
   float* mindist;          // nullable [N]
   double* inertia;         // nullable
+  long long* prof;         // nullable: [CTAs][16] cycle counters (scd_debug_set_name_profile), debugging aid
 };
 
 // host + device: byte offsets of the rings for a given plan
@@ -113,8 +115,7 @@ __device__ __forceinline__ bool es_better(float cand, float cur) {
 }
 
 __global__ void __launch_bounds__(kEsThreads, 1)
-estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_chi,
-                const __grid_constant__ CUtensorMap map_clo, const EsParams p) {
+estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c, const EsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = ptx::smem_u32(smem);
@@ -125,11 +126,18 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int kEsXStages = p.x_stages;
 
   auto bar = [&](int base, int i) { return sbase + L.tail_off + base + 8 * i; };
+  const bool prof = p.prof != nullptr;
+  long long* const pf = prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr;
+  auto twait = [&](uint32_t b, uint32_t parity, int tag, long long& acc) {
+    if (!prof) { ptx::mbar_wait(b, parity, tag); return; }
+    const long long c0 = clock64();
+    ptx::mbar_wait(b, parity, tag);
+    acc += clock64() - c0;
+  };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_x);
-    ptx::prefetch_tensormap(&map_chi);
-    ptx::prefetch_tensormap(&map_clo);
+    ptx::prefetch_tensormap(&map_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kEsXStages; ++s) { ptx::mbar_init(bar(EsTail::x_full, s), 1); ptx::mbar_init(bar(EsTail::x_empty, s), 4); }
@@ -151,43 +159,64 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L.tail_off + EsTail::tmem_ptr);
 
-  if (warp == 0) {
-    // =================================================== TMA producer
+  if (warp == 0 || warp == 3) {
+    // =================================================== X TMA producers (warp 0: even k-blocks, warp 3: odd)
+    // One warp gets one tensor box out of L2/HBM every ~400-550 cycles whatever its size, several warps issue
+    // independently (tools/tma_feed_bench.cu): with a single producer thread issuing X + hi + lo (72 boxes per row
+    // tile) this kernel sat at 0.51 of the HBM roofline, issue-bound.  Ring slots and parities derive from the
+    // running k-block index g, exactly as in the converters.
     if (lane == 0) {
-      int xs = 0, bs = 0; uint32_t xph = 0, bph = 0;
-      const uint32_t b_bytes = 2u * (uint32_t)p.n_tile * kEsBK * 2u;
+      const uint32_t me = warp == 0 ? 0u : 1u;
+      uint32_t g = 0;
+      long long w_xe = 0; const long long t0 = prof ? clock64() : 0;
       for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x) {
         for (int nt = 0; nt < p.n_ntiles; ++nt) {
-          for (int kb = 0; kb < nkb; ++kb) {
-            ptx::mbar_wait(bar(EsTail::x_empty, xs), xph ^ 1, 700 + xs);
+          for (int kb = 0; kb < nkb; ++kb, ++g) {
+            if ((g & 1u) != me) continue;
+            const uint32_t xs = g % kEsXStages, xph = (g / kEsXStages) & 1u;
+            twait(bar(EsTail::x_empty, xs), xph ^ 1, 700 + xs, w_xe);
             ptx::mbar_arrive_expect_tx(bar(EsTail::x_full, xs), kEsXBytes);
             ptx::tma_load_2d<1>(sbase + L.x_off + xs * kEsXBytes, &map_x, bar(EsTail::x_full, xs), kb * kEsBK, rt * kEsBM,
                                 p.n_ntiles > 1 ? ptx::kEvictNormal : ptx::kEvictFirst);
-            if (++xs == kEsXStages) { xs = 0; xph ^= 1; }
-            ptx::mbar_wait(bar(EsTail::b_empty, bs), bph ^ 1, 710 + bs);
-            ptx::mbar_arrive_expect_tx(bar(EsTail::b_full, bs), b_bytes);
-            const uint32_t bdst = sbase + L.b_off + bs * 2 * p.b_plane;
-            ptx::tma_load_2d<1>(bdst, &map_chi, bar(EsTail::b_full, bs), kb * kEsBK, nt * 256, ptx::kEvictLast);
-            ptx::tma_load_2d<1>(bdst + p.b_plane, &map_clo, bar(EsTail::b_full, bs), kb * kEsBK, nt * 256, ptx::kEvictLast);
-            if (++bs == kEsBStages) { bs = 0; bph ^= 1; }
           }
         }
       }
+      if (prof && warp == 0) { pf[0] = clock64() - t0; pf[1] = w_xe; }
+    }
+  } else if (warp == 2) {
+    // =================================================== centroid TMA producer: hi + lo planes in ONE 3-D box
+    if (lane == 0) {
+      const uint32_t b_bytes = 2u * (uint32_t)p.n_tile * kEsBK * 2u;
+      uint32_t g = 0;
+      long long w_be = 0;
+      for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x) {
+        for (int nt = 0; nt < p.n_ntiles; ++nt) {
+          for (int kb = 0; kb < nkb; ++kb, ++g) {
+            const uint32_t bs = g % kEsBStages, bph = (g / kEsBStages) & 1u;
+            twait(bar(EsTail::b_empty, bs), bph ^ 1, 710 + bs, w_be);
+            ptx::mbar_arrive_expect_tx(bar(EsTail::b_full, bs), b_bytes);
+            ptx::tma_load_3d(sbase + L.b_off + bs * 2 * p.b_plane, &map_c, bar(EsTail::b_full, bs), kb * kEsBK, nt * 256, 0,
+                             ptx::kEvictLast);
+          }
+        }
+      }
+      if (prof) pf[2] = w_be;
     }
   } else if (warp == 1) {
     // =================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc_bf16_f32(kEsBM, (uint32_t)p.n_tile);
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0, tile_no = 0;
+      long long w_te = 0, w_af = 0, w_bf = 0; const long long t0 = prof ? clock64() : 0;
       for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x) {
         for (int nt = 0; nt < p.n_ntiles; ++nt, ++tile_no) {
           const uint32_t buf = tile_no & 1u;
-          ptx::mbar_wait(bar(EsTail::t_empty, buf), ((tile_no >> 1) & 1u) ^ 1u, 720 + buf);
+          twait(bar(EsTail::t_empty, buf), ((tile_no >> 1) & 1u) ^ 1u, 720 + buf, w_te);
           ptx::tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + buf * 256;
           for (int kb = 0; kb < nkb; ++kb) {
-            ptx::mbar_wait(bar(EsTail::a_full, as), aph, 730 + as);
-            ptx::mbar_wait(bar(EsTail::b_full, bs), bph, 740 + bs);
+            twait(bar(EsTail::a_full, as), aph, 730 + as, w_af);
+            twait(bar(EsTail::b_full, bs), bph, 740 + bs, w_bf);
             ptx::tc_fence_after_sync();
             const uint32_t a_hi = sbase + L.a_off + as * 2 * kEsAPlane, a_lo = a_hi + kEsAPlane;
             const uint32_t b_hi = sbase + L.b_off + bs * 2 * p.b_plane, b_lo = b_hi + p.b_plane;
@@ -208,6 +237,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           ptx::umma_commit<1>(bar(EsTail::t_full, buf), 0);
         }
       }
+      if (prof) { pf[3] = clock64() - t0; pf[4] = w_te; pf[5] = w_af; pf[6] = w_bf; pf[11] = tile_no; }
     }
   } else if (warp >= 4 && warp < 4 + 4 * kEsConvSets) {
     // =================================================== converters: fp32 tile -> bf16 hi / lo operand tiles
@@ -219,6 +249,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     float* xnorm_s = reinterpret_cast<float*>(smem + L.tail_off + EsTail::xnorm);
     uint32_t g = 0;                       // running k-block index: ring slots and parities derive from it
     uint32_t my_tile = 0;                 // row tiles this CTA has converted: ||x||^2 slot = my_tile & 3
+    long long w_xf = 0, w_ae = 0; const long long t0c = prof ? clock64() : 0;
     for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x, ++my_tile) {
       for (int nt = 0; nt < p.n_ntiles; ++nt) {
         float norm = 0.f;
@@ -226,7 +257,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if ((int)(g % kEsConvSets) != cset) continue;
           const uint32_t xs = g % kEsXStages, xph = (g / kEsXStages) & 1u;
           const uint32_t as = g % kEsAStages, aph = (g / kEsAStages) & 1u;
-          ptx::mbar_wait(bar(EsTail::x_full, xs), xph, 750 + xs);
+          twait(bar(EsTail::x_full, xs), xph, 750 + xs, w_xf);
           const uint8_t* xt = smem + L.x_off + xs * kEsXBytes + x_row;
           float4 f[8];
 #pragma unroll
@@ -251,7 +282,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             hi[c] = make_uint4(h[0], h[1], h[2], h[3]);
             lo[c] = make_uint4(l[0], l[1], l[2], l[3]);
           }
-          ptx::mbar_wait(bar(EsTail::a_empty, as), aph ^ 1, 760 + as);
+          twait(bar(EsTail::a_empty, as), aph ^ 1, 760 + as, w_ae);
           uint8_t* at = smem + L.a_off + as * 2 * kEsAPlane + a_row;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -267,6 +298,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
       }
     }
+    if (prof && warp == 4 && lane == 0) { pf[7] = clock64() - t0c; pf[8] = w_xf; pf[9] = w_ae; }
   } else if (warp >= 4 + 4 * kEsConvSets) {
     // =================================================== epilogue: running argmin per row
     const uint32_t quad = warp & 3u;
@@ -276,6 +308,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const float* xnorm_s = reinterpret_cast<const float*>(smem + L.tail_off + EsTail::xnorm);
     uint32_t tile_no = 0, my_tile = 0;
     double inertia_local = 0.0;
+    long long w_tf = 0;
     // the converters run at most 2 accumulator tiles + 3 operand stages ahead of this warp, so the
     // 4-deep ||x||^2 ring (slot = row tiles done & 3) is never overwritten before it is read
     for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x, ++my_tile) {
@@ -283,7 +316,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       float xn = 0.f;
       for (int nt = 0; nt < p.n_ntiles; ++nt, ++tile_no) {
         const uint32_t buf = tile_no & 1u;
-        ptx::mbar_wait(bar(EsTail::t_full, buf), (tile_no >> 1) & 1u, 770 + buf);
+        twait(bar(EsTail::t_full, buf), (tile_no >> 1) & 1u, 770 + buf, w_tf);
         ptx::tc_fence_after_sync();
         if (nt == 0) {
 #pragma unroll
@@ -319,6 +352,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         inertia_local += (double)d;
       }
     }
+    if (prof && warp == 4 + 4 * kEsConvSets && lane == 0) pf[10] = w_tf;
     if (p.inertia) {
       for (int off = 16; off > 0; off >>= 1) inertia_local += __shfl_down_sync(0xffffffffu, inertia_local, off);
       if (lane == 0) atomicAdd(p.inertia, inertia_local);

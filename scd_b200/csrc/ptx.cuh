@@ -163,6 +163,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* desc,
   }
 }
 
+// 3-D tile load (single-CTA form): used to bring the hi and lo centroid planes in with one instruction
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* desc, uint32_t bar, int c0, int c1, int c2, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05
 template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_result_addr, uint32_t ncols) {

@@ -95,6 +95,23 @@ int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols
   return 0;
 }
 
+// two bf16 planes [2][rows, cols] `plane_bytes` apart as one 3-D tensor, box = [2][box_rows][box_cols], SWIZZLE_64B
+int make_map_planes(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t plane_bytes, uint32_t box_rows,
+                    uint32_t box_cols) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {cols, rows, 2};
+  cuuint64_t strides[2] = {cols * 2u, plane_bytes};
+  cuuint32_t box[3] = {box_cols, box_rows, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (planes) failed with CUresult %d (rows=%llu cols=%llu)", (int)r,
+                                     (unsigned long long)rows, (unsigned long long)cols);
+  return 0;
+}
+
 // ---------------------------------------------------------------- naming plan
 struct NamePlan {
   int kt;                 // compiled list length (1, 5 or 8)
@@ -220,12 +237,13 @@ int scd_estep(const float* X, int64_t N, int D, const float* C, int K, int64_t* 
   p.labels = reinterpret_cast<long long*>(labels);
   p.mindist = mindist;
   p.inertia = inertia_acc;
-  CUtensorMap mx, mhi, mlo;
+  p.prof = g_name_prof;
+  CUtensorMap mx, mc;
   if (int e = make_map_2d(&mx, X, (uint64_t)N, (uint64_t)D, scd::kEsBM, scd::kEsBK, CU_TENSOR_MAP_SWIZZLE_128B, true)) return e;
-  if (int e = make_map_2d(&mhi, chi, (uint64_t)K, (uint64_t)D, (uint32_t)p.n_tile, scd::kEsBK, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
-  if (int e = make_map_2d(&mlo, clo, (uint64_t)K, (uint64_t)D, (uint32_t)p.n_tile, scd::kEsBK, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+  // hi and lo planes as one 3-D tensor [2][K][D]: a single box brings both k-slabs of a stage
+  if (int e = make_map_planes(&mc, chi, (uint64_t)K, (uint64_t)D, plane, (uint32_t)p.n_tile, scd::kEsBK)) return e;
   // shared-memory plan: the centroid ring takes what n_tile needs, the rest goes to fp32 X stages in flight
-  p.b_plane = (int)align_up((size_t)p.n_tile * scd::kEsBK * 2, 1024);
+  p.b_plane = p.n_tile * scd::kEsBK * 2;          // n_tile % 16 == 0 -> a multiple of 1024 (swizzle-atom aligned)
   {
     const int fixed = scd::EsLayout(0, p.b_plane).total + 1024;
     p.x_stages = std::max(2, std::min(scd::kEsMaxXStages, (scd::kEsSmemLimit - fixed) / scd::kEsXBytes));
@@ -238,7 +256,7 @@ int scd_estep(const float* X, int64_t N, int D, const float* C, int K, int64_t* 
     attr_smem = smem;
   }
   const int grid = std::min(device_sm_count(), p.n_row_tiles);
-  scd::estep_tc_kernel<<<grid, scd::kEsThreads, smem, st>>>(mx, mhi, mlo, p);
+  scd::estep_tc_kernel<<<grid, scd::kEsThreads, smem, st>>>(mx, mc, p);
   SCD_LAUNCH_CHECK("estep_tc_kernel");
   return 0;
 }

@@ -161,6 +161,37 @@ def step_name_prof():
     print('per-pair issuer total (first 10):', p[:10, 0].tolist())
 
 
+def step_estep_prof():
+    """Cycle counters of the E-step kernel's warp roles (scd_debug_set_name_profile)."""
+    import torch
+    from scd_b200 import kmeans, _lib
+    for (n, d, k) in [(127000, 768, 100), (127000, 768, 1000)]:
+        X = torch.randn(n, d, device='cuda'); X = X / X.norm(dim=1, keepdim=True)
+        C = X[:k].clone()
+        labels = torch.empty(n, dtype=torch.int64, device='cuda'); acc = torch.zeros(1, dtype=torch.float64, device='cuda')
+        for _ in range(2):
+            kmeans._estep(X, C, labels, acc)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            kmeans._estep(X, C, labels, acc)
+        e1.record(); torch.cuda.synchronize()
+        print(f'estep n={n} k={k}: {e0.elapsed_time(e1)/5*1e3:.1f} us (incl. centroid split)')
+        prof = torch.zeros(148, 16, dtype=torch.int64, device='cuda')
+        _lib.load().scd_debug_set_name_profile(prof.data_ptr())
+        kmeans._estep(X, C, labels, acc)
+        torch.cuda.synchronize()
+        _lib.load().scd_debug_set_name_profile(None)
+        p = prof.cpu().double()
+        names = {0: 'X producer total', 1: 'X producer wait x_empty', 2: 'C producer wait b_empty', 3: 'issuer total', 4: 'issuer wait t_empty',
+                 5: 'issuer wait a_full', 6: 'issuer wait b_full', 7: 'converter total', 8: 'converter wait x_full', 9: 'converter wait a_empty',
+                 10: 'epilogue wait t_full', 11: 'tiles'}
+        for kk, nm in names.items():
+            col = p[:, kk]
+            print(f'   {nm:28s} mean={col.mean():12.0f} min={col.min():12.0f} max={col.max():12.0f}')
+
+
 STEPS = ['kmeans', 'naming_tiny', 'naming_shapes', 'vote', 'naming_time']
 
 if __name__ == '__main__':
