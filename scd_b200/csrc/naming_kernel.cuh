@@ -6,47 +6,64 @@
 //   replaces  main_unsup.py:519-529 / main_ptsup.py:538-543 (GEMM -> [1024, V] logits in HBM ->
 //   softmax -> topk twice) and main_unsup.py:610-614 (k = 1 over the K selected columns).
 //
-// The N x V score matrix never exists: a CTA pair (cta_group::2, 256 x 256 x 16 tcgen05.mma) keeps its
-// 256 image rows stationary in shared memory (2 x 12 k-blocks x 16 KB, SWIZZLE_128B), streams the
-// vocabulary through a 4-stage TMA ring (SWIZZLE_64B, 32 k per stage), accumulates each
-// 256 x 256 tile in TMEM (2 x 256 columns, double buffered) and the four epilogue warps read the
-// tile back with tcgen05.ld - one thread per image row.  The epilogue is a two-level selection: per
-// 32-column chunk only the chunk maximum is computed (31 FMNMX) and compared with the row's k-th best
-// chunk maximum; the rare chunk that beats it is parked (32 floats) in an L2-resident scratch slot.
-// The true top-k of a row lies inside its k chunks with the largest maxima, so one exact scan of
-// those k parked chunks at the end of the vocabulary sweep finishes the row.  (The unsupervised
+// The N x V score matrix never exists: a CTA pair (cta_group::2, 256 x 192 x 16 tcgen05.mma) keeps its 256 image
+// rows stationary for a whole vocabulary sweep, streams the vocabulary through a deep TMA ring, accumulates each
+// 256 x 192 tile in TMEM (double buffered) and eight epilogue warps read the tile back with tcgen05.ld - one
+// thread per image row.
+//
+// Operand placement is what the measurements forced (profiles/r1_name_cycle_counters.txt, r1_tma_feed.txt): a
+// vocabulary box needs ~600 cycles from L2 plus ~400 cycles of barrier round trips, so the ring must hold >= 3
+// k-blocks ahead of the tensor pipe; with all 192 KB of stationary rows in shared memory only 32 KB (2 k-blocks) were
+// left and the issuer spent 40 % of its time waiting for B (65 % tensor-active).  Now the first four 64-wide
+// k-blocks of the rows live in TENSOR MEMORY as the A operand (tcgen05.mma with A from TMEM; loader warps write them
+// with tcgen05.st, thread = row = TMEM lane), the other eight stay in shared memory (SWIZZLE_128B), and the 96 KB
+// that frees hold an 8-deep ring of 96-row x 64-k vocabulary boxes (12 KB, SWIZZLE_128B).  TMEM: accumulators at
+// columns [0,192) and [256,448), A k-blocks at [192,256) and [448,512).
+//
+// The epilogue is a two-level selection: per 32-column chunk only the chunk maximum is computed (31 FMNMX) and
+// compared with the row's k-th best chunk maximum; the rare chunk that beats it is parked (32 floats) in an
+// L2-resident scratch slot.  The true top-k of a row lies inside its k chunks with the largest maxima, so one
+// exact scan of those k parked chunks at the end of the vocabulary sweep finishes the row.  (The unsupervised
 // driver's softmax additionally keeps a running max / sum-exp.)  Only [N, k] leaves the SM.
 //
-// Warp roles (384 threads): 0 = vocabulary (B) TMA producer, 1 = MMA issuer (leader CTA only), 2 = TMEM
-// allocator, 3 = image-row (A) TMA producer, 4..11 = epilogue (TMEM lane quadrant = warp & 3; warps
-// 4..7 take columns 0..127 of every accumulator tile, warps 8..11 columns 128..255, so each scheduler
-// has two epilogue warps to interleave).  The single-thread issue loops (MMA, TMA) probe the NEXT
-// stage's mbarrier with a non-blocking test_wait before they issue the current stage's work, so the
-// ~100-cycle barrier round trip is off the critical path (ncu, round 1: the issuer, not the tensor
-// pipe, was the bottleneck at 55 % tensor-active).
+// Warp roles (512 threads): 0, 2 = vocabulary (B) TMA producers (alternate k-blocks; 2 also allocates TMEM),
+// 1, 3 = MMA issuers (leader CTA only, alternate k-blocks), 4..11 = epilogue (TMEM lane quadrant = warp & 3; warps
+// 4..7 take columns 0..95 of every accumulator tile, warps 8..11 columns 96..191), 12..15 = loaders of the
+// TMEM-resident A k-blocks (global -> registers -> tcgen05.st); 12 is also the TMA producer of the shared-memory
+// A k-blocks.
 #pragma once
 #include "ptx.cuh"
 #include <cuda_bf16.h>
 
 namespace scd {
 
-constexpr int kNameMaxD = 768;         // widest embedding the stationary A buffer holds (any D <= 768, D % 8 == 0)
+constexpr int kNameMaxD = 768;         // widest embedding the stationary A operand holds (any D <= 768, D % 8 == 0)
 constexpr int kBlockM = 128;           // rows per CTA (256 per pair)
-constexpr int kTileN = 256;            // vocabulary entries per accumulator tile (128 loaded per CTA)
-constexpr int kAKBlock = 64;           // k per stationary A block  (128 B rows, SWIZZLE_128B)
+constexpr int kTileN = 192;            // vocabulary entries per accumulator tile (96 loaded per CTA)
+constexpr int kAKBlock = 64;           // k per A / B block  (128 B rows, SWIZZLE_128B)
 constexpr int kNumAKBlocks = kNameMaxD / kAKBlock;   // 12 (capacity; the live count is NameParams::num_kb)
-constexpr int kBK = 32;                // k per B stage            (64 B rows, SWIZZLE_64B)
-constexpr int kBStages = 4;
+constexpr int kTmemAKBlocks = 4;       // A k-blocks 0..3 live in tensor memory (32 columns each)
+constexpr int kSmemAKBlocks = kNumAKBlocks - kTmemAKBlocks;   // 8 in shared memory
+constexpr int kBStages = 8;            // one stage = one k-block (12 KB) of one vocabulary tile
+constexpr int kBProducers = 2;         // warps 0 and 2 issue alternate stages (one warp keeps only one box in flight,
+                                       // ~500-600 cycles each: tools/tma_feed_bench.cu)
 constexpr int kABlockBytes = kBlockM * kAKBlock * 2;     // 16384
-constexpr int kBStageBytes = (kTileN / 2) * kBK * 2;     // 8192 per CTA
-constexpr int kNameThreads = 384;
+constexpr int kBStageBytes = (kTileN / 2) * kAKBlock * 2;   // 12288 per CTA
+constexpr int kNumIssuers = 3;          // MMA issuer warps 1, 3 and 16, round-robin over k-blocks
+constexpr int kNameThreads = 544;
 constexpr int kEpiHalves = 2;           // column halves of a tile, one epilogue warp set each
+constexpr int kHalfCols = kTileN / kEpiHalves;   // 96
 constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;         // accumulator buffer b starts at column b * 256
+
+// first TMEM column of A k-block kb (kb < kTmemAKBlocks): the 64 columns above each accumulator buffer
+__host__ __device__ constexpr int a_tmem_col(int kb) { return kTileN + (kb & 1) * 32 + (kb >> 1) * kAccStride; }
+static_assert(kTileN + 64 <= kAccStride && kHalfCols % 32 == 0, "TMEM column plan");
 
 struct NameSmem {
   // offsets inside dynamic shared memory (base aligned to 1024)
   static constexpr int a_off = 0;
-  static constexpr int b_off = kNumAKBlocks * kABlockBytes;                 // 196608
+  static constexpr int b_off = kSmemAKBlocks * kABlockBytes;                // 131072
   static constexpr int bar_off = b_off + kBStages * kBStageBytes;           // 229376
   // barriers (8 B each)
   static constexpr int full_bar = bar_off;                                  // [kBStages]
@@ -56,9 +73,10 @@ struct NameSmem {
   static constexpr int tmem_full_bar = a_empty_bar + 8 * kNumAKBlocks;      // [2]
   static constexpr int tmem_empty_bar = tmem_full_bar + 16;                 // [2]
   static constexpr int tmem_ptr = tmem_empty_bar + 16;
-  static constexpr int total = tmem_ptr + 16;
+  static constexpr int issue_seq = tmem_ptr + 16;                           // k-blocks issued so far (the issuers' token)
+  static constexpr int total = issue_seq + 16;
 };
-static_assert(NameSmem::total <= 232448, "exceeds 227 KB of shared memory");
+static_assert(NameSmem::total + 1024 <= 232448, "exceeds 227 KB of shared memory");
 
 struct NameParams {
   long long n_rows;        // N
@@ -80,6 +98,8 @@ struct NameParams {
   float* part_sum;
   float* scratch;          // [gridDim.x][2 halves][128 rows][KT slots][32] parked chunks
   long long* prof;         // nullable: [pairs][16] cycle counters (scd_debug_set_name_profile), debugging aid
+  const __nv_bfloat16* x;  // [N, d] row-major: the loader warps read the TMEM-resident k-blocks straight from global memory
+  int d;
 };
 
 // One sorted top-KT list in registers, ordered by (value descending, column ascending) - the order
@@ -147,7 +167,9 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   // SWIZZLE_128B tiles need a 1024-aligned base; both CTAs of the pair compute the same offset
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = ptx::smem_u32(smem);
-  const uint32_t warp = threadIdx.x >> 5;
+  // the shuffle makes the warp index provably warp-uniform for ptxas: role loops then run on the uniform datapath
+  // (descriptor arithmetic in UIADD3 instead of vector math + R2UR in front of every tcgen05.mma)
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t cta_rank = ptx::cluster_ctarank();
   const bool leader = cta_rank == 0;
@@ -157,6 +179,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const int tiles_total = (int)((p.v_total + kTileN - 1) / kTileN);
 
   const int nkb = p.num_kb;
+  const int nkb_tmem = min(nkb, kTmemAKBlocks);
   auto full_bar = [&](int s) { return sbase + NameSmem::full_bar + 8 * s; };
   auto empty_bar = [&](int s) { return sbase + NameSmem::empty_bar + 8 * s; };
   auto a_full_bar = [&](int kb) { return sbase + NameSmem::a_full_bar + 8 * kb; };
@@ -170,11 +193,16 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kBStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-    for (int kb = 0; kb < kNumAKBlocks; ++kb) { ptx::mbar_init(a_full_bar(kb), 1); ptx::mbar_init(a_empty_bar(kb), 1); }
+    for (int kb = 0; kb < kNumAKBlocks; ++kb) {
+      // TMEM-resident k-blocks: the four loader warps of both CTAs arrive; shared-memory k-blocks: one expect_tx
+      ptx::mbar_init(a_full_bar(kb), kb < kTmemAKBlocks ? 8 : 1);
+      ptx::mbar_init(a_empty_bar(kb), 1);
+    }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(tmem_full_bar(b), 1);
       ptx::mbar_init(tmem_empty_bar(b), 16);     // 8 epilogue warps x 2 CTAs arrive on the leader's copy
     }
+    *reinterpret_cast<volatile uint32_t*>(smem + NameSmem::issue_seq) = 0u;
     ptx::fence_mbar_init_cluster();
   }
   if (warp == 2) {
@@ -198,7 +226,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   };
   // Staggered sweep: pair q starts its walk over an item's tiles at a different offset and wraps around, so
   // at any moment the 74 pairs read 74 different vocabulary tiles (spread over all L2 slices) instead of
-  // all hammering the same 16 KB.  The result does not depend on the visiting order (explicit tie rules).
+  // all hammering the same lines.  The result does not depend on the visiting order (explicit tie rules).
   auto item_tile = [&](int it, int t) {
     const int nt = item_ntiles(it);
     const int start = (int)(((long long)pair * nt) / n_pairs);
@@ -207,96 +235,161 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     return item_tile0(it) + tt;
   };
 
-  if (warp == 0) {
-    // ======================================================= vocabulary (B) TMA producer
-    // Whole warp runs the loop (warp-uniform control flow keeps addresses in uniform registers); one
-    // elected lane issues.  `free_next` is a non-blocking probe of the next stage's empty barrier made
-    // before this stage's TMA goes out.
-    static_assert(kBStages % 2 == 0 && kAKBlock == 2 * kBK, "the B ring is consumed two stages (one k-block) at a time");
-    // Refill is per stage (a slot is reloaded the moment its two MMAs retire), consumption per k-block.
-    int stage = 0; uint32_t phase = 0;
+  if (warp == 0 || warp == 2) {
+    // ======================================================= vocabulary (B) TMA producers
+    // Stage g (a running count over the whole kernel) belongs to producer g % 2.  Whole warp runs the loop
+    // (warp-uniform control flow keeps addresses in uniform registers); one elected lane issues.
+    const uint32_t me = warp == 0 ? 0u : 1u;
+    uint32_t g = 0;
+    const bool prof = p.prof != nullptr;
+    long long pf_t0 = prof ? clock64() : 0, pf_e = 0;
     for (int it = pair; it < n_items; it += n_pairs) {
       const int nt = item_ntiles(it);
       for (int t = 0; t < nt; ++t) {
         const int v0 = item_tile(it, t) * kTileN + (int)cta_rank * (kTileN / 2);
-        for (int ks = 0; ks < nkb * (kAKBlock / kBK); ++ks) {
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1, 200 + stage);
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          if ((g % kBProducers) != me) continue;
+          const int stage = (int)(g % kBStages);
+          const uint32_t phase = (g / kBStages) & 1u;
+          { const long long c0 = prof ? clock64() : 0;
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1, 200 + stage);
+            if (prof) pf_e += clock64() - c0; }
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * kBStageBytes);
             ptx::tma_load_2d<2>(sbase + NameSmem::b_off + stage * kBStageBytes, &map_w,
-                                full_bar(stage) & ptx::kPeerBitMask, ks * kBK, v0, ptx::kEvictLast);
+                                full_bar(stage) & ptx::kPeerBitMask, kb * kAKBlock, v0, ptx::kEvictLast);
           }
           __syncwarp();
-          if (++stage == kBStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 3) {
-    // ======================================================= image-row (A) TMA producer
-    // The pair's 256 rows stay in shared memory for a whole work item; k-block kb of the NEXT item is
-    // loaded as soon as the last tile of the current item has consumed it (a_empty, committed by the MMA
-    // issuer), i.e. while that last tile is still running.
+    if (prof && lane == 0) {
+      long long* o = p.prof + (size_t)pair * 32;
+      const int base = (leader ? 0 : 16) + 6 + 6 * (int)me;         // leader: 6,7 / 12,13; peer: 22,23 / 28,29
+      o[base] = clock64() - pf_t0; o[base + 1] = pf_e;
+    }
+  } else if (warp >= 12 && warp < 16) {
+    // ======================================================= loaders of the TMEM-resident A k-blocks
+    // thread = image row = TMEM lane; one k-block = 64 bf16 = 32 packed columns.  Global loads of a k-block are in
+    // flight before the wait for its columns to be released by the previous item's last tile.
+    const uint32_t quad = warp & 3u;
+    const uint32_t lane_addr = (quad * 32u) << 16;
     int my_item_no = 0;
     for (int it = pair; it < n_items; it += n_pairs, ++my_item_no) {
-      const int row0 = item_rb(it) * 2 * kBlockM + (int)cta_rank * kBlockM;
-      for (int kb = 0; kb < nkb; ++kb) {
-        ptx::mbar_wait(a_empty_bar(kb), (my_item_no & 1) ^ 1, 100 + kb);
-        if (ptx::elect_one()) {
-          if (leader) ptx::mbar_arrive_expect_tx(a_full_bar(kb), 2 * kABlockBytes);
-          ptx::tma_load_2d<2>(sbase + NameSmem::a_off + kb * kABlockBytes, &map_x,
-                              a_full_bar(kb) & ptx::kPeerBitMask, kb * kAKBlock, row0, ptx::kEvictFirst);
+      const long long row = (long long)item_rb(it) * 2 * kBlockM + cta_rank * kBlockM + quad * 32 + lane;
+      const uint4* src = reinterpret_cast<const uint4*>(p.x + (size_t)(row < p.n_rows ? row : 0) * p.d);
+      for (int kb = 0; kb < nkb_tmem; ++kb) {
+        uint32_t r[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (row < p.n_rows && kb * kAKBlock + q * 8 < p.d) v = __ldg(src + kb * 8 + q);
+          r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
         }
+        ptx::mbar_wait(a_empty_bar(kb), (my_item_no & 1) ^ 1, 150 + kb);
+        ptx::tc_fence_after_sync();
+        ptx::tmem_st_32x32(tmem_base + lane_addr + a_tmem_col(kb), r);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
         __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_remote(a_full_bar(kb) & ptx::kPeerBitMask);
+      }
+      // warp 12 is also the TMA producer of the shared-memory A k-blocks: k-block kb >= kTmemAKBlocks of the NEXT item
+      // is loaded as soon as the last tile of the current item has consumed it (a_empty, committed by the MMA issuer)
+      if (warp == 12) {
+        const int row0 = item_rb(it) * 2 * kBlockM + (int)cta_rank * kBlockM;
+        for (int kb = kTmemAKBlocks; kb < nkb; ++kb) {
+          ptx::mbar_wait(a_empty_bar(kb), (my_item_no & 1) ^ 1, 100 + kb);
+          if (ptx::elect_one()) {
+            if (leader) ptx::mbar_arrive_expect_tx(a_full_bar(kb), 2 * kABlockBytes);
+            ptx::tma_load_2d<2>(sbase + NameSmem::a_off + (kb - kTmemAKBlocks) * kABlockBytes, &map_x,
+                                a_full_bar(kb) & ptx::kPeerBitMask, kb * kAKBlock, row0, ptx::kEvictFirst);
+          }
+          __syncwarp();
+        }
       }
     }
-  } else if (warp == 1) {
-    // ======================================================= MMA issuer (leader CTA; one elected lane issues)
+  } else if (warp == 1 || warp == 3 || warp == 16) {
+    // ======================================================= MMA issuers (leader CTA; one elected lane of each issues)
+    // What the measurements say about issuing (tools/mma_rate_bench.cu, profiles/r1_mma_rate_*.txt): the tensor pipe
+    // runs an MMA in exactly N/2 cycles when the next one is already queued, the queue is only a couple of MMAs deep,
+    // and a tcgen05.mma keeps the uniform registers of its descriptors busy until it has run - so an issuer that
+    // prepares the next k-block's descriptors after its own MMAs does so behind an idle pipe (+43 cycles per MMA).
+    // Two warps therefore take alternate k-blocks (running count g): each has its own uniform registers, computes
+    // its descriptors and does its barrier waits while the other warp's four MMAs run, then waits for a named-barrier
+    // token (ids 1 / 2) and fires its four MMAs back to back.  The token keeps the issue order, which is also the
+    // execution order of the pipe, so the last k-block's commit covers the whole tile.
     if (leader) {
+      const uint32_t me = warp == 1 ? 0u : (warp == 3 ? 1u : 2u);
       const uint32_t idesc = ptx::make_idesc_bf16_f32(2 * kBlockM, kTileN);
-      int stage = 0; uint32_t phase = 0;
-      uint32_t tile_no = 0;
+      uint32_t g = 0, tile_no = 0;
       int my_item_no = 0;
-      const bool prof = p.prof != nullptr;
-      long long pf_t0 = prof ? clock64() : 0, pf_te = 0, pf_a = 0, pf_b = 0;
+      long long g_total = 0;
+      for (int it = pair; it < n_items; it += n_pairs) g_total += (long long)item_ntiles(it) * nkb;
+      const bool prof = p.prof != nullptr && me == 0;
+      long long pf_t0 = prof ? clock64() : 0, pf_te = 0, pf_a = 0, pf_b = 0, pf_tok = 0;
+      long long* const trace = (p.prof != nullptr && pair == 0 && me < 2) ? p.prof + (size_t)n_pairs * 32 + me * 384 : nullptr;
+      int n_ev = 0;
       for (int it = pair; it < n_items; it += n_pairs, ++my_item_no) {
         const int nt = item_ntiles(it);
         for (int t = 0; t < nt; ++t, ++tile_no) {
           const uint32_t buf = tile_no & 1u;
-          { const long long c0 = prof ? clock64() : 0;
-            ptx::mbar_wait(tmem_empty_bar(buf), ((tile_no >> 1) & 1u) ^ 1u, 300 + buf);
-            if (prof) pf_te += clock64() - c0; }
-          const uint32_t d_tmem = tmem_base + buf * kTileN;
-          for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t d_tmem = tmem_base + buf * kAccStride;
+          for (int kb = 0; kb < nkb; ++kb, ++g) {
+            if ((g % kNumIssuers) != me) continue;
+            const int stage = (int)(g % kBStages);
+            const uint32_t phase = (g / kBStages) & 1u;
+            // operands of the four MMAs, ready in registers before the token arrives
+            const bool a_in_tmem = kb < kTmemAKBlocks;
+            const uint32_t b_addr = sbase + NameSmem::b_off + stage * kBStageBytes;
+            const uint32_t a_addr = sbase + NameSmem::a_off + (a_in_tmem ? 0 : kb - kTmemAKBlocks) * kABlockBytes;
+            uint64_t bd[4], ad[4];
+            uint32_t at[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              bd[kk] = ptx::make_kmajor_desc(b_addr + kk * 32, 128);
+              ad[kk] = ptx::make_kmajor_desc(a_addr + kk * 32, 128);
+              at[kk] = tmem_base + a_tmem_col(a_in_tmem ? kb : 0) + kk * 8;
+              asm volatile("" : "+l"(bd[kk]), "+l"(ad[kk]), "+r"(at[kk]));
+            }
+            if (kb == 0) { const long long c0 = prof ? clock64() : 0;
+              ptx::mbar_wait(tmem_empty_bar(buf), ((tile_no >> 1) & 1u) ^ 1u, 300 + buf);
+              if (prof) pf_te += clock64() - c0; }
             if (t == 0) { const long long c0 = prof ? clock64() : 0;
               ptx::mbar_wait(a_full_bar(kb), my_item_no & 1, 400 + kb);
               if (prof) pf_a += clock64() - c0; }
-            const uint32_t a_addr = sbase + NameSmem::a_off + kb * kABlockBytes;
-            // one k-block = two B stages: both full barriers are probed together, then four MMAs go out
             { const long long c0 = prof ? clock64() : 0;
-              ptx::mbar_wait2(full_bar(stage), full_bar(stage + 1), phase, 500 + stage);
+              ptx::mbar_wait(full_bar(stage), phase, 500 + stage);
               if (prof) pf_b += clock64() - c0; }
             ptx::tc_fence_after_sync();
-            if (ptx::elect_one()) {
+            const long long tr0 = trace ? clock64() : 0;
+            // token: the previous issuer has issued k-block g - 1
+            if (g > 0) { const long long c0 = prof ? clock64() : 0;
+              ptx::named_bar_sync(1 + me, 64);
+              if (prof) pf_tok += clock64() - c0; }
+            const long long tr1 = trace ? clock64() : 0;
+            const bool elected = ptx::elect_one();
+            if (elected) {
+              if (a_in_tmem) {
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint32_t b_addr = sbase + NameSmem::b_off + (stage + h) * kBStageBytes;
+                for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16_ts<2>(d_tmem, at[kk], bd[kk], idesc, (kb | kk) != 0 ? 1u : 0u);
+              } else {
 #pragma unroll
-                for (int kk = 0; kk < kBK / 16; ++kk) {
-                  const uint64_t adesc = ptx::make_kmajor_desc(a_addr + (h * kBK + kk * 16) * 2, 128);
-                  const uint64_t bdesc = ptx::make_kmajor_desc(b_addr + kk * 16 * 2, 64);
-                  ptx::umma_bf16<2>(d_tmem, adesc, bdesc, idesc, (kb | h | kk) != 0 ? 1u : 0u);
-                }
-                ptx::umma_commit<2>(empty_bar(stage + h), 0b11);
+                for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16<2>(d_tmem, ad[kk], bd[kk], idesc, 1u);
               }
+            }
+            __syncwarp();
+            if ((long long)g + 1 < g_total) ptx::named_bar_arrive(1 + (me + 1) % kNumIssuers, 64);     // hand the token over ...
+            if (elected) {                                                                            // ... then commit
+              ptx::umma_commit<2>(empty_bar(stage), 0b11);
               if (t == nt - 1) ptx::umma_commit<2>(a_empty_bar(kb), 0b11);
               if (kb == nkb - 1) ptx::umma_commit<2>(tmem_full_bar(buf), 0b11);
             }
             __syncwarp();
-            stage += 2;
-            if (stage == kBStages) { stage = 0; phase ^= 1; }
+            if (trace && lane == 0 && n_ev < 128) { trace[3 * n_ev] = tr0; trace[3 * n_ev + 1] = tr1; trace[3 * n_ev + 2] = clock64(); ++n_ev; }
           }
         }
-        if (nt == 0) {       // an item without tiles still has to hand its A buffers back
+        if (nt == 0 && me == 0) {       // an item without tiles still has to hand its A buffers back
           for (int kb = 0; kb < nkb; ++kb) {
             ptx::mbar_wait(a_full_bar(kb), my_item_no & 1, 450 + kb);
             if (ptx::elect_one()) ptx::umma_commit<2>(a_empty_bar(kb), 0b11);
@@ -305,22 +398,23 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
       }
       if (prof && lane == 0) {
-        long long* o = p.prof + (size_t)pair * 16;
-        o[0] = clock64() - pf_t0; o[1] = pf_te; o[2] = pf_a; o[3] = pf_b; o[4] = 0; o[5] = tile_no;
+        long long* o = p.prof + (size_t)pair * 32;
+        o[0] = clock64() - pf_t0; o[1] = pf_te; o[2] = pf_a; o[3] = pf_b; o[4] = pf_tok; o[5] = tile_no;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 12) {
     // ======================================================= epilogue: one thread per image row
     const uint32_t quad = warp & 3u;                 // TMEM lane quadrant this warp may read
     const uint32_t half = (warp - 4u) >> 2;          // column half of every tile this warp scans
     const uint32_t lane_addr = (quad * 32u) << 16;
-    constexpr int kHalfCols = kTileN / kEpiHalves;   // 128
     uint32_t tile_no = 0;
     ChunkTop<KT> ctop;
     float4* const my_scratch = reinterpret_cast<float4*>(p.scratch) +
                                (((size_t)blockIdx.x * kEpiHalves + half) * kBlockM + quad * 32 + lane) * KT * 8;   // KT slots x 8 float4
     const bool prof = p.prof != nullptr && warp == 4 && leader;
     long long pf_t0 = prof ? clock64() : 0, pf_w = 0, pf_fin = 0;
+    long long* const trace = (prof && pair == 0) ? p.prof + (size_t)n_pairs * 32 + 2 * 384 : nullptr;
+    int n_ev = 0;
     for (int it = pair; it < n_items; it += n_pairs) {
       const int nt = item_ntiles(it);
       const long long row = (long long)item_rb(it) * 2 * kBlockM + cta_rank * kBlockM + quad * 32 + lane;
@@ -365,25 +459,25 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           ptx::mbar_wait(tmem_full_bar(buf), (tile_no >> 1) & 1u, 600 + buf);
           if (prof) pf_w += clock64() - c0; }
         ptx::tc_fence_after_sync();
-        const uint32_t taddr = tmem_base + lane_addr + buf * kTileN + half * kHalfCols;
+        const long long tr0 = trace ? clock64() : 0;
+        const uint32_t taddr = tmem_base + lane_addr + buf * kAccStride + half * kHalfCols;
+        static_assert(kHalfCols == 96, "the epilogue below walks three 32-column chunks");
         uint32_t ra[32], rb[32];
         ptx::tmem_ld_32x32(taddr, ra);
-#pragma unroll 1
-        for (int c = 0; c < kHalfCols / 32; c += 2) {
-          ptx::tmem_ld_wait(ra);                                 // ra = chunk c
-          ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);          // in flight while ra is processed
-          process(ra, col0 + c * 32, n_valid - c * 32);
-          ptx::tmem_ld_wait(rb);                                 // rb = chunk c + 1
-          if (c + 2 < kHalfCols / 32) {
-            ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
-          } else {
-            // this warp's share of the accumulator buffer is in registers: hand it back to the MMA issuer
-            ptx::tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_remote(tmem_empty_bar(buf) & ptx::kPeerBitMask);
-          }
-          process(rb, col0 + (c + 1) * 32, n_valid - (c + 1) * 32);
-        }
+        ptx::tmem_ld_wait(ra);                                   // ra = chunk 0
+        ptx::tmem_ld_32x32(taddr + 32, rb);                      // in flight while ra is processed
+        process(ra, col0, n_valid);
+        ptx::tmem_ld_wait(rb);                                   // rb = chunk 1
+        ptx::tmem_ld_32x32(taddr + 64, ra);
+        process(rb, col0 + 32, n_valid - 32);
+        ptx::tmem_ld_wait(ra);                                   // ra = chunk 2
+        // this warp's share of the accumulator buffer is in registers: hand it back to the MMA issuer
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_remote(tmem_empty_bar(buf) & ptx::kPeerBitMask);
+        const long long tr1 = trace ? clock64() : 0;
+        process(ra, col0 + 64, n_valid - 64);
+        if (trace && lane == 0 && n_ev < 128) { trace[3 * n_ev] = tr0; trace[3 * n_ev + 1] = tr1; trace[3 * n_ev + 2] = clock64(); ++n_ev; }
       }
 
       // Exact top-k of the row from its (at most KT) parked chunks, in two divergence-free passes (a naive
@@ -438,7 +532,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       if (prof) pf_fin += clock64() - pf_c1;
     }
     if (prof && lane == 0) {
-      long long* o = p.prof + (size_t)pair * 16;
+      long long* o = p.prof + (size_t)pair * 32;
       o[8] = clock64() - pf_t0; o[9] = pf_w; o[10] = pf_fin;
     }
   }

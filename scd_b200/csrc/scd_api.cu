@@ -424,7 +424,7 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
 
   CUtensorMap mx, mw;
   if (int e = make_map_2d(&mx, X, (uint64_t)N, (uint64_t)D, scd::kBlockM, scd::kAKBlock, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  if (int e = make_map_2d(&mw, Wt, (uint64_t)V, (uint64_t)D, scd::kTileN / 2, scd::kBK, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+  if (int e = make_map_2d(&mw, Wt, (uint64_t)V, (uint64_t)D, scd::kTileN / 2, scd::kAKBlock, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
 
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
   scd::NameParams p;
@@ -443,6 +443,8 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
   p.part_sum = reinterpret_cast<float*>(w8 + pl.off_sum);
   p.scratch = reinterpret_cast<float*>(w8 + pl.off_scratch);
   p.prof = g_name_prof;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(X);
+  p.d = D;
   if (pl.n_vsplit > 1) SCD_CUDA(cudaMemsetAsync(p.part_idx, 0xFF, pl.idx_bytes, st));   // -1: "row has nothing in this part"
 
   int e = 0;

@@ -146,19 +146,33 @@ def step_name_prof():
     vocab = naming.Vocabulary.from_rows(W)
     for _ in range(2):
         naming.name_topk_raw(X, vocab, 5, False)
-    prof = torch.zeros(74, 16, dtype=torch.int64, device='cuda')
+    prof = torch.zeros(74 * 32 + 4 * 384, dtype=torch.int64, device='cuda')
     _lib.load().scd_debug_set_name_profile(prof.data_ptr())
     naming.name_topk_raw(X, vocab, 5, False)
     torch.cuda.synchronize()
     _lib.load().scd_debug_set_name_profile(None)
-    p = prof.cpu().double()
+    full = prof.cpu()
+    p = full[:74 * 32].view(74, 32).double()
     names = {0: 'issuer total', 1: 'issuer wait tmem_empty', 2: 'issuer wait a_full', 3: 'issuer wait b_full (blocking)',
-             4: 'issuer b-not-ready events', 5: 'tiles', 8: 'epi total', 9: 'epi wait tmem_full', 10: 'epi item-final scan'}
+             4: 'issuer wait token', 5: 'tiles', 6: 'B producer 0 total', 7: 'B producer 0 wait empty', 12: 'B producer 1 total', 13: 'B producer 1 wait empty', 23: 'peer B producer 0 wait empty', 29: 'peer B producer 1 wait empty',
+             14: 'issuer b waits > 150 cyc (count)', 15: 'issuer b waits > 150 cyc (cycles)', 16: 'issuer longest b wait',
+             8: 'epi total', 9: 'epi wait tmem_full', 10: 'epi item-final scan'}
     for k, nm in names.items():
         col = p[:, k]
         print(f'{nm:32s} mean={col.mean():12.0f} min={col.min():12.0f} max={col.max():12.0f}')
-    print('issuer busy-issue cycles per tile:', float(((p[:, 0] - p[:, 1] - p[:, 2] - p[:, 3]) / p[:, 5]).mean()))
+    print('issuer busy-issue cycles per tile:', float(((p[:, 0] - p[:, 1] - p[:, 2] - p[:, 3] - p[:, 4]) / p[:, 5]).mean()))
     print('per-pair issuer total (first 10):', p[:10, 0].tolist())
+    tr = full[74 * 32:].view(4, 128, 3)
+    t0 = int(tr[0, 0, 0])
+    print('trace pair 0 (cycles since first event): issuer0 / issuer1 runs: ready, token, issued')
+    for i in range(30, 48):
+        a, b = tr[0, i].tolist(), tr[1, i].tolist()
+        print(f'  run {i}: I0 ready {a[0]-t0:8d} tok {a[1]-t0:8d} issued {a[2]-t0:8d} (issue {a[2]-a[1]:5d}) | I1 ready {b[0]-t0:8d} tok {b[1]-t0:8d} issued {b[2]-t0:8d} (issue {b[2]-b[1]:5d})')
+    print('epilogue warp 4: tile full-seen, released, done')
+    for i in range(4, 12):
+        a = tr[2, i].tolist()
+        print(f'  tile {i}: full {a[0]-t0:8d} released {a[1]-t0:8d} (+{a[1]-a[0]}) done {a[2]-t0:8d} (+{a[2]-a[0]})')
+    print('producer 0 issue times:', [int(tr[3, i, 0]) - t0 for i in range(24, 44)])
 
 
 def step_estep_prof():
