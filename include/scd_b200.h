@@ -58,6 +58,21 @@ SCD_API int scd_estep(const float* X, int64_t N, int D, const float* C, int K,
               int64_t* labels, float* mindist /* nullable */, double* inertia_acc /* nullable */, int exact,
               void* ws, size_t ws_bytes, scd_stream_t stream);
 
+/* k-means++ seeding, faster_mix_k_means_pytorch.py:20-36 (gcd copy :82-110), without the per-centre N x c distance
+ * matrix and without a host round trip per centre:
+ *   scd_kpp_update: d2[i] = min(d2[i], ||X_i - X[*pick]||^2) (first != 0: plain assignment), center_out[:] = X[*pick]
+ *                   (nullable), per-block fp64 sums of d2 into ws; *pick < 0 leaves d2 as it is;
+ *   scd_kpp_select: the reference's draw  prob = d2/sum(d2); ind = first i with cumsum(prob)[i] >= r  (:31-34) resolved
+ *                   on the device with fp64 prefix sums; when no row qualifies *pick keeps its value and *no_hit |= 1
+ *                   (|= 2 if *pick < 0, i.e. nothing to reuse; sticky, the caller zeroes it once): the gcd copy
+ *                   :104-107 reuses the previous index, the local copy :34 raises IndexError.
+ *                   sums_valid = 0 recomputes the block sums from d2 first (d2 produced by scd_estep's mindist). */
+SCD_API size_t scd_kpp_workspace_bytes(int64_t N);
+SCD_API int scd_kpp_update(const float* X, int64_t N, int D, const int64_t* pick, int first, float* d2,
+                   float* center_out /* nullable, [D] */, void* ws, size_t ws_bytes, scd_stream_t stream);
+SCD_API int scd_kpp_select(const float* d2, int64_t N, int sums_valid, double r, int64_t* pick, int32_t* no_hit,
+                   void* ws, size_t ws_bytes, scd_stream_t stream);
+
 /* Labelled-row inertia, faster_mix_k_means_pytorch.py:108-109: *acc += sum_i ||L[i]-C[labels[i]]||^2. */
 SCD_API int scd_labelled_inertia(const float* L, const int64_t* labels, int64_t n, int D, const float* C, int K,
                          double* acc, scd_stream_t stream);

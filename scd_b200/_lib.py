@@ -21,6 +21,9 @@ SIGNATURES = {
     'scd_pairwise_distance': (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp]),
     'scd_estep_workspace_bytes': (_sz, [_int, _int]),
     'scd_estep': (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
+    'scd_kpp_workspace_bytes': (_sz, [_i64]),
+    'scd_kpp_update': (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _sz, _vp]),
+    'scd_kpp_select': (_int, [_vp, _i64, _int, C.c_double, _vp, _vp, _vp, _sz, _vp]),
     'scd_labelled_inertia': (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp, _vp]),
     'scd_mstep_workspace_bytes': (_sz, [_i64, _int]),
     'scd_mstep_sums': (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _sz, _vp]),

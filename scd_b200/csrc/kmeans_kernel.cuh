@@ -360,4 +360,118 @@ gather_sqdist_kernel(const float* __restrict__ L, const long long* __restrict__ 
   }
 }
 
+// --------------------------------------------------------------------------------------------
+// a5 k-means++ seeding, faster_mix_k_means_pytorch.py:20-36 (gcd copy :82-110).  The reference recomputes the full
+// N x c distance matrix for every added centre; here a running min-distance vector d2[N] is updated against the newest
+// centre only (kpp_update_kernel: one pass over X per centre, block sums of d2 in fp64) and the draw is resolved on the
+// device (kpp_select_kernel): prob = d2 / sum(d2), first index with cumsum(prob) >= r  <=>  first index whose prefix
+// sum of d2 reaches r * sum(d2) (fp64 prefix sums; the reference's fp32 cumsum is only accurate to a few rows' worth of
+// probability mass at N ~ 1e5, so the picked row can differ within that margin - DESIGN 4).  The picked row index
+// never visits the host: the next update reads it from device memory.
+// --------------------------------------------------------------------------------------------
+constexpr int kKppRowsPerBlock = 64;     // 8 warps x 8 rows
+
+// d2[i] = min(d2[i], ||X_i - X[*pick]||^2)  (first == 1: no min, plain assignment);  also centers_out[:] = X[*pick].
+// *pick < 0 (no candidate was found by the select step) leaves d2 untouched and only refreshes the block sums.
+__global__ void __launch_bounds__(256)
+kpp_update_kernel(const float* __restrict__ X, long long N, int D, const long long* __restrict__ pick, int first,
+                  float* __restrict__ d2, double* __restrict__ block_sums, float* __restrict__ center_out) {
+  const long long src = *pick;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* c = X + (src >= 0 ? src : 0) * D;
+  if (blockIdx.x == 0 && center_out && src >= 0)
+    for (int d = threadIdx.x; d < D; d += blockDim.x) center_out[d] = c[d];
+  double local = 0.0;
+  for (int r = 0; r < kKppRowsPerBlock / 8; ++r) {
+    const long long row = (long long)blockIdx.x * kKppRowsPerBlock + warp * (kKppRowsPerBlock / 8) + r;
+    if (row >= N) break;
+    float part = 0.f;
+    if (src >= 0) {
+      const float* x = X + row * D;
+      for (int d = lane; d < D; d += 32) { const float df = x[d] - c[d]; part = fmaf(df, df, part); }
+      for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    }
+    if (lane == 0) {
+      float v = d2[row];
+      if (src >= 0) { v = first ? part : fminf(v, part); d2[row] = v; }
+      local += (double)v;
+    }
+  }
+  __shared__ double sh[8];
+  if (lane == 0) sh[warp] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    block_sums[blockIdx.x] = t;
+  }
+}
+
+// block sums of an existing d2 vector (seeding from several pre-centres: d2 comes from the E-step's mindist)
+__global__ void __launch_bounds__(256)
+kpp_block_sums_kernel(const float* __restrict__ d2, long long N, double* __restrict__ block_sums) {
+  const long long base = (long long)blockIdx.x * kKppRowsPerBlock;
+  double v = 0.0;
+  if (threadIdx.x < kKppRowsPerBlock && base + threadIdx.x < N) v = (double)d2[base + threadIdx.x];
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  __shared__ double sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = sh[0] + sh[1];
+}
+
+// one block: total = sum(block_sums); target = r * total; first row whose inclusive prefix sum of d2 >= target.
+// *pick is left unchanged when no row qualifies (r beyond the last cumulative value, or total is 0 / NaN) and
+// *no_hit gets bit 0 (sticky; bit 1 as well when there is no previous pick to fall back on) - the gcd copy reuses the previous index (:104-107), the local copy raises IndexError (:34).
+__global__ void __launch_bounds__(1024)
+kpp_select_kernel(const float* __restrict__ d2, long long N, const double* __restrict__ block_sums, int n_blocks, double r,
+                  long long* __restrict__ pick, int* __restrict__ no_hit) {
+  __shared__ double sh[1024];
+  __shared__ double s_total;
+  __shared__ int s_block;
+  __shared__ double s_before;
+  // total, in a fixed order
+  double t = 0.0;
+  for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) t += block_sums[b];
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int off = 512; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { s_total = sh[0]; s_block = -1; s_before = 0.0; }
+  __syncthreads();
+  const double total = s_total;
+  const double target = r * total;
+  if (!(total > 0.0)) {                       // 0 / 0 probabilities are NaN in the reference: nothing compares >= r
+    if (threadIdx.x == 0) atomicOr(no_hit, 1 | (*pick < 0 ? 2 : 0));
+    return;
+  }
+  // first block whose inclusive prefix reaches the target: thread 0 walks the (few thousand) block sums
+  if (threadIdx.x == 0) {
+    double run = 0.0;
+    for (int b = 0; b < n_blocks; ++b) {
+      const double nxt = run + block_sums[b];
+      if (nxt >= target) { s_block = b; s_before = run; break; }
+      run = nxt;
+    }
+  }
+  __syncthreads();
+  if (s_block < 0) {
+    if (threadIdx.x == 0) atomicOr(no_hit, 1 | (*pick < 0 ? 2 : 0));
+    return;
+  }
+  if (threadIdx.x == 0) {
+    const long long base = (long long)s_block * kKppRowsPerBlock;
+    double run = s_before;
+    long long found = -1;
+    for (int i = 0; i < kKppRowsPerBlock && base + i < N; ++i) {
+      run += (double)d2[base + i];
+      if (run >= target) { found = base + i; break; }
+    }
+    if (found < 0) found = min(base + kKppRowsPerBlock, N) - 1;      // rounding between the two summation orders
+    *pick = found;
+  }
+}
+
 }  // namespace scd

@@ -261,6 +261,40 @@ int scd_estep(const float* X, int64_t N, int D, const float* C, int K, int64_t* 
   return 0;
 }
 
+// ---------------------------------------------------------------------------- k-means++ seeding (a5)
+size_t scd_kpp_workspace_bytes(int64_t N) {
+  const size_t nb = (size_t)((std::max<int64_t>(N, 1) + scd::kKppRowsPerBlock - 1) / scd::kKppRowsPerBlock);
+  return align_up(nb * sizeof(double), 256) + 256;
+}
+
+int scd_kpp_update(const float* X, int64_t N, int D, const int64_t* pick, int first, float* d2, float* center_out, void* ws,
+                   size_t ws_bytes, scd_stream_t stream) {
+  if (N <= 0 || D <= 0) return fail("scd_kpp_update: bad shape N=%lld D=%d", (long long)N, D);
+  if (!X || !pick || !d2 || !ws) return fail("scd_kpp_update: null pointer");
+  if (ws_bytes < scd_kpp_workspace_bytes(N)) return fail("scd_kpp_update: workspace too small");
+  const int nb = (int)((N + scd::kKppRowsPerBlock - 1) / scd::kKppRowsPerBlock);
+  scd::kpp_update_kernel<<<nb, 256, 0, as_stream(stream)>>>(X, N, D, reinterpret_cast<const long long*>(pick), first, d2,
+                                                            reinterpret_cast<double*>(ws), center_out);
+  SCD_LAUNCH_CHECK("kpp_update_kernel");
+  return 0;
+}
+
+int scd_kpp_select(const float* d2, int64_t N, int sums_valid, double r, int64_t* pick, int32_t* no_hit, void* ws, size_t ws_bytes,
+                   scd_stream_t stream) {
+  if (N <= 0) return fail("scd_kpp_select: bad shape N=%lld", (long long)N);
+  if (!d2 || !pick || !no_hit || !ws) return fail("scd_kpp_select: null pointer");
+  if (ws_bytes < scd_kpp_workspace_bytes(N)) return fail("scd_kpp_select: workspace too small");
+  const int nb = (int)((N + scd::kKppRowsPerBlock - 1) / scd::kKppRowsPerBlock);
+  cudaStream_t st = as_stream(stream);
+  if (!sums_valid) {
+    scd::kpp_block_sums_kernel<<<nb, 256, 0, st>>>(d2, N, reinterpret_cast<double*>(ws));
+    SCD_LAUNCH_CHECK("kpp_block_sums_kernel");
+  }
+  scd::kpp_select_kernel<<<1, 1024, 0, st>>>(d2, N, reinterpret_cast<const double*>(ws), nb, r, reinterpret_cast<long long*>(pick), no_hit);
+  SCD_LAUNCH_CHECK("kpp_select_kernel");
+  return 0;
+}
+
 int scd_labelled_inertia(const float* L, const int64_t* labels, int64_t n, int D, const float* C, int K, double* acc,
                          scd_stream_t stream) {
   if (n < 0 || D <= 0 || K <= 0) return fail("scd_labelled_inertia: bad shape");

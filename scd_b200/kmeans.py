@@ -199,36 +199,43 @@ class K_Means:
     def kpp(self, X, pre_centers=None, k=10, random_state=None):
         """k-means++ seeding, ``faster_mix_k_means_pytorch.py:20-36`` (gcd copy :82-110 with the "no
         candidate" guard).  Keeps a running min-distance vector and only measures the newly added centre
-        (one N x D pass per centre instead of the reference's N x c x D); draws ``r = random_state.rand()``
-        from the same host RNG stream, one draw per centre, and takes the first index with
-        ``cumsum(d2 / sum(d2)) >= r``."""
+        (``scd_kpp_update``: one N x D pass per centre instead of the reference's N x c x D); draws
+        ``r = random_state.rand()`` from the same host RNG stream, one draw per centre, and resolves
+        ``first index with cumsum(d2 / sum(d2)) >= r`` on the device (``scd_kpp_select``).  The picked row index
+        stays on the device, so the whole seeding is a stream of launches with a single host sync at the end."""
         rs = check_random_state(random_state)
         Xd = _dev_f32(X)
+        n, d = int(Xd.shape[0]), int(Xd.shape[1])
+        dev = Xd.device
         if pre_centers is not None:
-            Cc = _dev_f32(pre_centers).view(-1, Xd.shape[1])
+            Cc = _dev_f32(pre_centers).view(-1, d)
         else:
             Cc = Xd[rs.randint(0, len(Xd))].view(1, -1)                            # :25
-        centers = torch.empty(max(k, Cc.shape[0]), Xd.shape[1], dtype=torch.float32, device=Xd.device)
-        n_have = Cc.shape[0]
+        centers = torch.empty(max(k, Cc.shape[0]), d, dtype=torch.float32, device=dev)
+        n_have = int(Cc.shape[0])
         centers[:n_have] = Cc
-        if n_have >= k:
+        if n_have >= k or n == 0:
             return centers[:n_have]
-        d2 = pairwise_distance(Xd, centers[:n_have], out_device=Xd.device).min(dim=1).values     # :28-30
-        ind = None
+        lib = _lib.load()
+        ws = torch.empty(lib.scd_kpp_workspace_bytes(n), dtype=torch.uint8, device=dev)
+        d2 = torch.empty(n, dtype=torch.float32, device=dev)
+        pick = torch.full((1,), -1, dtype=torch.int64, device=dev)
+        no_hit = torch.zeros(1, dtype=torch.int32, device=dev)
+        # distances to the centres we start from (:28-30): fused fp32 E-step, min-distance output only
+        scratch_labels = torch.empty(n, dtype=torch.int64, device=dev)
+        _estep(Xd, centers[:n_have].contiguous(), scratch_labels, None, mindist=d2, exact=True)
+        sums_valid = 0
         while n_have < k:
-            prob = d2 / d2.sum()                                                   # :31
-            cum = torch.cumsum(prob, dim=0)                                        # :32
-            r = rs.rand()                                                          # :33
-            hit = cum >= r
-            if bool(hit.any()):
-                ind = int(torch.argmax(hit.to(torch.uint8)))                       # :34 first index
-            elif ind is None:
-                # gcd copy :104-107 silently reuses the previous index; with none yet, both copies fail
-                raise IndexError('kpp: no cumulative probability reached the draw (reference :34)')
-            centers[n_have] = Xd[ind]                                              # :35
-            newd = pairwise_distance(Xd, centers[n_have:n_have + 1], out_device=Xd.device).view(-1)
-            d2 = torch.minimum(d2, newd)
+            r = float(rs.rand())                                                   # :33 (one host draw per added centre)
+            _lib.check(lib.scd_kpp_select(d2.data_ptr(), n, sums_valid, r, pick.data_ptr(), no_hit.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), _stream()), 'scd_kpp_select')                          # :31-34
+            _lib.check(lib.scd_kpp_update(Xd.data_ptr(), n, d, pick.data_ptr(), 0, d2.data_ptr(), centers[n_have].data_ptr(),
+                                          ws.data_ptr(), ws.numel(), _stream()), 'scd_kpp_update')           # :35 + next :28-30
+            sums_valid = 1
             n_have += 1
+        if int(no_hit.item()) & 2:                                                 # the one host sync of the seeding
+            # gcd copy :104-107 silently reuses the previous index; with none yet, both copies fail
+            raise IndexError('kpp: no cumulative probability reached the draw (reference :34)')
         return centers[:n_have]
 
     def fit_once(self, X, random_state):

@@ -213,3 +213,82 @@ def test_full_size_c2_properties():
     ms.finalize(Cd, cn)
     sub = labels.cpu() == 7
     assert torch.allclose(cn[7].cpu(), X[sub].double().mean(0).float(), atol=ATOL)
+
+
+def _kpp_select(d2, r, pick0=-1, sums_valid=0):
+    from scd_b200 import _lib
+    lib = _lib.load()
+    n = d2.numel()
+    ws = torch.empty(lib.scd_kpp_workspace_bytes(n), dtype=torch.uint8, device='cuda')
+    pick = torch.full((1,), pick0, dtype=torch.int64, device='cuda')
+    no_hit = torch.zeros(1, dtype=torch.int32, device='cuda')
+    _lib.check(lib.scd_kpp_select(d2.data_ptr(), n, sums_valid, float(r), pick.data_ptr(), no_hit.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  torch.cuda.current_stream().cuda_stream), 'scd_kpp_select')
+    return int(pick.item()), int(no_hit.item())
+
+
+@pytest.mark.parametrize('n', [1, 63, 64, 65, 1000, 127000])
+def test_kpp_select_is_the_first_index_whose_cumulative_probability_reaches_r(n):
+    """ref :31-34 ``prob = d2 / d2.sum(); ind = (cumsum(prob) >= r).nonzero()[0][0]`` in exact (fp64) arithmetic."""
+    g = torch.Generator().manual_seed(n)
+    d2 = torch.rand(n, generator=g) ** 3
+    d2[torch.rand(n, generator=g) < 0.2] = 0.0            # already-chosen rows have zero distance
+    if n > 1:
+        d2[0] = 0.0
+    cum = np.cumsum(d2.double().numpy())
+    total = cum[-1]
+    for r in [0.0, 1e-9, 0.1, 0.37, 0.5, 0.731, 0.999999, float(np.nextafter(1.0, 0.0))]:
+        if total == 0:
+            break
+        want = int(np.searchsorted(cum, r * total, side='left'))
+        got, miss = _kpp_select(d2.cuda(), r)
+        assert miss == 0
+        if got != want:        # the two fp64 summation orders may disagree only where the target sits on a boundary
+            assert abs(got - want) <= 1 and abs(cum[min(got, want)] - r * total) <= 1e-9 * total, (n, r, got, want)
+
+
+def test_kpp_select_without_candidate_keeps_the_previous_pick():
+    d2 = torch.zeros(500, device='cuda')                  # every row coincides with a centre: 0/0 probabilities
+    assert _kpp_select(d2, 0.3, pick0=-1) == (-1, 3)      # nothing to reuse -> the caller raises IndexError (ref :34)
+    assert _kpp_select(d2, 0.3, pick0=17) == (17, 1)      # gcd copy :104-107 reuses the previous index
+    X = torch.ones(40, 8)
+    with pytest.raises(IndexError):
+        kmeans.K_Means(k=3).kpp(X.cuda(), k=3, random_state=0)
+
+
+def test_kpp_update_tracks_the_running_min_distance():
+    from scd_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(4)
+    n, d = 3000, 96
+    X = synth.unit_rows(torch.randn(n, d, generator=g))
+    Xd = X.cuda()
+    ws = torch.empty(lib.scd_kpp_workspace_bytes(n), dtype=torch.uint8, device='cuda')
+    d2 = torch.empty(n, device='cuda')
+    centre = torch.empty(d, device='cuda')
+    want = None
+    for step, idx in enumerate([5, 2999, 1234]):
+        pick = torch.tensor([idx], dtype=torch.int64, device='cuda')
+        _lib.check(lib.scd_kpp_update(Xd.data_ptr(), n, d, pick.data_ptr(), int(step == 0), d2.data_ptr(), centre.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), 'scd_kpp_update')
+        dist = kmeans_oracle.pairwise_distance(X, X[idx:idx + 1], None).view(-1)
+        want = dist if want is None else torch.minimum(want, dist)
+        assert (d2.cpu() - want).abs().max() < 1e-5
+        assert torch.equal(centre.cpu(), X[idx])
+        sums = ws[:((n + 63) // 64) * 8].view(torch.float64).cpu()
+        assert abs(float(sums.sum()) - float(d2.double().sum())) < 1e-9 * max(1.0, float(sums.sum()))
+        assert _kpp_select(d2, 0.5, sums_valid=1) == _kpp_select(d2, 0.5, sums_valid=0)      # the update's block sums are what select needs
+
+
+def test_kpp_seeding_spreads_like_the_reference_at_scale():
+    """20 000 x 768, 30 centres: every pick is a data row, no duplicates, and the seeding potential (sum of min
+    distances) is within 2 % of what the oracle's seeding reaches with the same RNG stream."""
+    X, _ = synth.image_feats(20000, 40, seed=77)
+    got = kmeans.K_Means(k=30).kpp(X.cuda(), k=30, random_state=3).cpu()
+    want = kmeans_oracle.K_Means(k=30, pairwise_batch_size=4096).kpp(X, k=30, random_state=3)
+    assert got.shape == want.shape == (30, 768)
+    assert torch.unique(got, dim=0).shape[0] == 30
+    pot = lambda C: float(kmeans_oracle.pairwise_distance(X, C, 4096).min(dim=1).values.sum())
+    assert abs(pot(got) - pot(want)) < 0.02 * pot(want)
+    same = ((got - want).abs().max(dim=1).values < 1e-6).float().mean()
+    assert same >= 0.5            # identical draws pick identical rows unless a draw lands within fp32-cumsum error of a boundary
