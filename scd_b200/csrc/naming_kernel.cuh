@@ -39,32 +39,32 @@ namespace scd {
 
 constexpr int kNameMaxD = 768;         // widest embedding the stationary A operand holds (any D <= 768, D % 8 == 0)
 constexpr int kBlockM = 128;           // rows per CTA (256 per pair)
-constexpr int kTileN = 192;            // vocabulary entries per accumulator tile (96 loaded per CTA)
+constexpr int kTileN = 240;            // vocabulary entries per accumulator tile (120 loaded per CTA)
 constexpr int kAKBlock = 64;           // k per A / B block  (128 B rows, SWIZZLE_128B)
 constexpr int kNumAKBlocks = kNameMaxD / kAKBlock;   // 12 (capacity; the live count is NameParams::num_kb)
-constexpr int kTmemAKBlocks = 4;       // A k-blocks 0..3 live in tensor memory (32 columns each)
+constexpr int kTmemAKBlocks = 1;       // A k-block 0 lives in tensor memory (2 x 16 columns, above each accumulator)
 constexpr int kSmemAKBlocks = kNumAKBlocks - kTmemAKBlocks;   // 8 in shared memory
-constexpr int kBStages = 8;            // one stage = one k-block (12 KB) of one vocabulary tile
+constexpr int kBStages = 3;            // one stage = one k-block (15 KB) of one vocabulary tile
 constexpr int kBProducers = 2;         // warps 0 and 2 issue alternate stages (one warp keeps only one box in flight,
                                        // ~500-600 cycles each: tools/tma_feed_bench.cu)
 constexpr int kABlockBytes = kBlockM * kAKBlock * 2;     // 16384
-constexpr int kBStageBytes = (kTileN / 2) * kAKBlock * 2;   // 12288 per CTA
+constexpr int kBStageBytes = (kTileN / 2) * kAKBlock * 2;   // 15360 per CTA
 constexpr int kNumIssuers = 3;          // MMA issuer warps 1, 3 and 16, round-robin over k-blocks
 constexpr int kNameThreads = 544;
 constexpr int kEpiHalves = 2;           // column halves of a tile, one epilogue warp set each
-constexpr int kHalfCols = kTileN / kEpiHalves;   // 96
+constexpr int kHalfCols = 128;          // epilogue warps 4..7 take columns [0,128), warps 8..11 columns [128,240)
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;         // accumulator buffer b starts at column b * 256
 
-// first TMEM column of A k-block kb (kb < kTmemAKBlocks): the 64 columns above each accumulator buffer
-__host__ __device__ constexpr int a_tmem_col(int kb) { return kTileN + (kb & 1) * 32 + (kb >> 1) * kAccStride; }
-static_assert(kTileN + 64 <= kAccStride && kHalfCols % 32 == 0, "TMEM column plan");
+// TMEM column of the kk-th 16-wide k-step of the TMEM-resident A k-block: 16 columns above each accumulator buffer
+__host__ __device__ constexpr int a_tmem_col(int kk) { return kTileN + (kk >> 1) * kAccStride + (kk & 1) * 8; }
+static_assert(kTileN + 16 <= kAccStride && kTmemAKBlocks == 1, "TMEM column plan");
 
 struct NameSmem {
   // offsets inside dynamic shared memory (base aligned to 1024)
   static constexpr int a_off = 0;
-  static constexpr int b_off = kSmemAKBlocks * kABlockBytes;                // 131072
-  static constexpr int bar_off = b_off + kBStages * kBStageBytes;           // 229376
+  static constexpr int b_off = kSmemAKBlocks * kABlockBytes;                // 180224
+  static constexpr int bar_off = b_off + kBStages * kBStageBytes;           // 226304
   // barriers (8 B each)
   static constexpr int full_bar = bar_off;                                  // [kBStages]
   static constexpr int empty_bar = full_bar + 8 * kBStages;                 // [kBStages]
@@ -288,7 +288,8 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         ptx::mbar_wait(a_empty_bar(kb), (my_item_no & 1) ^ 1, 150 + kb);
         ptx::tc_fence_after_sync();
-        ptx::tmem_st_32x32(tmem_base + lane_addr + a_tmem_col(kb), r);
+        ptx::tmem_st_32x16(tmem_base + lane_addr + a_tmem_col(0), r);            // k 0..31  -> columns above buffer 0
+        ptx::tmem_st_32x16(tmem_base + lane_addr + a_tmem_col(2), r + 16);       // k 32..63 -> columns above buffer 1
         ptx::tmem_st_wait();
         ptx::tc_fence_before_sync();
         __syncwarp();
@@ -349,7 +350,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             for (int kk = 0; kk < 4; ++kk) {
               bd[kk] = ptx::make_kmajor_desc(b_addr + kk * 32, 128);
               ad[kk] = ptx::make_kmajor_desc(a_addr + kk * 32, 128);
-              at[kk] = tmem_base + a_tmem_col(a_in_tmem ? kb : 0) + kk * 8;
+              at[kk] = tmem_base + a_tmem_col(kk);
               asm volatile("" : "+l"(bd[kk]), "+l"(ad[kk]), "+r"(at[kk]));
             }
             if (kb == 0) { const long long c0 = prof ? clock64() : 0;
@@ -454,14 +455,16 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       for (int t = 0; t < nt; ++t, ++tile_no) {
         const uint32_t buf = tile_no & 1u;
         const int col0 = item_tile(it, t) * kTileN + (int)half * kHalfCols;
-        const int n_valid = (int)min((long long)kHalfCols, p.v_total - col0);      // may be <= 0 on the last tile
+        const int half_cols = half == 0 ? kHalfCols : kTileN - kHalfCols;
+        const int n_valid = (int)min((long long)half_cols, p.v_total - col0);      // may be <= 0 on the last tile
         { const long long c0 = prof ? clock64() : 0;
           ptx::mbar_wait(tmem_full_bar(buf), (tile_no >> 1) & 1u, 600 + buf);
           if (prof) pf_w += clock64() - c0; }
         ptx::tc_fence_after_sync();
         const long long tr0 = trace ? clock64() : 0;
         const uint32_t taddr = tmem_base + lane_addr + buf * kAccStride + half * kHalfCols;
-        static_assert(kHalfCols == 96, "the epilogue below walks three 32-column chunks");
+        // four 32-column chunks per half; the second half has 112 columns (its last chunk reads 16 columns of the
+        // TMEM-resident A operand, masked by n_valid)
         uint32_t ra[32], rb[32];
         ptx::tmem_ld_32x32(taddr, ra);
         ptx::tmem_ld_wait(ra);                                   // ra = chunk 0
@@ -471,12 +474,15 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         ptx::tmem_ld_32x32(taddr + 64, ra);
         process(rb, col0 + 32, n_valid - 32);
         ptx::tmem_ld_wait(ra);                                   // ra = chunk 2
+        ptx::tmem_ld_32x32(taddr + 96, rb);
+        process(ra, col0 + 64, n_valid - 64);
+        ptx::tmem_ld_wait(rb);                                   // rb = chunk 3
         // this warp's share of the accumulator buffer is in registers: hand it back to the MMA issuer
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_remote(tmem_empty_bar(buf) & ptx::kPeerBitMask);
         const long long tr1 = trace ? clock64() : 0;
-        process(ra, col0 + 64, n_valid - 64);
+        process(rb, col0 + 96, n_valid - 96);
         if (trace && lane == 0 && n_ev < 128) { trace[3 * n_ev] = tr0; trace[3 * n_ev + 1] = tr1; trace[3 * n_ev + 2] = clock64(); ++n_ev; }
       }
 
