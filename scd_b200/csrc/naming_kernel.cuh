@@ -39,32 +39,32 @@ namespace scd {
 
 constexpr int kNameMaxD = 768;         // widest embedding the stationary A operand holds (any D <= 768, D % 8 == 0)
 constexpr int kBlockM = 128;           // rows per CTA (256 per pair)
-constexpr int kTileN = 240;            // vocabulary entries per accumulator tile (120 loaded per CTA)
+constexpr int kTileN = 224;            // vocabulary entries per accumulator tile (112 loaded per CTA)
 constexpr int kAKBlock = 64;           // k per A / B block  (128 B rows, SWIZZLE_128B)
 constexpr int kNumAKBlocks = kNameMaxD / kAKBlock;   // 12 (capacity; the live count is NameParams::num_kb)
-constexpr int kTmemAKBlocks = 1;       // A k-block 0 lives in tensor memory (2 x 16 columns, above each accumulator)
+constexpr int kTmemAKBlocks = 2;       // A k-blocks 0, 1 live in tensor memory (32 columns above each accumulator)
 constexpr int kSmemAKBlocks = kNumAKBlocks - kTmemAKBlocks;   // 8 in shared memory
-constexpr int kBStages = 3;            // one stage = one k-block (15 KB) of one vocabulary tile
+constexpr int kBStages = 4;            // one stage = one k-block (14 KB) of one vocabulary tile
 constexpr int kBProducers = 2;         // warps 0 and 2 issue alternate stages (one warp keeps only one box in flight,
                                        // ~500-600 cycles each: tools/tma_feed_bench.cu)
 constexpr int kABlockBytes = kBlockM * kAKBlock * 2;     // 16384
-constexpr int kBStageBytes = (kTileN / 2) * kAKBlock * 2;   // 15360 per CTA
+constexpr int kBStageBytes = (kTileN / 2) * kAKBlock * 2;   // 14336 per CTA
 constexpr int kNumIssuers = 3;          // MMA issuer warps 1, 3 and 16, round-robin over k-blocks
 constexpr int kNameThreads = 544;
 constexpr int kEpiHalves = 2;           // column halves of a tile, one epilogue warp set each
-constexpr int kHalfCols = 128;          // epilogue warps 4..7 take columns [0,128), warps 8..11 columns [128,240)
+constexpr int kHalfCols = 128;          // epilogue warps 4..7 take columns [0,128), warps 8..11 columns [128,224)
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;         // accumulator buffer b starts at column b * 256
 
-// TMEM column of the kk-th 16-wide k-step of the TMEM-resident A k-block: 16 columns above each accumulator buffer
-__host__ __device__ constexpr int a_tmem_col(int kk) { return kTileN + (kk >> 1) * kAccStride + (kk & 1) * 8; }
-static_assert(kTileN + 16 <= kAccStride && kTmemAKBlocks == 1, "TMEM column plan");
+// TMEM column of the kk-th 16-wide k-step of TMEM-resident A k-block kb: the 32 columns above accumulator buffer kb
+__host__ __device__ constexpr int a_tmem_col(int kb, int kk) { return kTileN + kb * kAccStride + kk * 8; }
+static_assert(kTileN + 32 <= kAccStride && kTmemAKBlocks == 2, "TMEM column plan");
 
 struct NameSmem {
   // offsets inside dynamic shared memory (base aligned to 1024)
   static constexpr int a_off = 0;
-  static constexpr int b_off = kSmemAKBlocks * kABlockBytes;                // 180224
-  static constexpr int bar_off = b_off + kBStages * kBStageBytes;           // 226304
+  static constexpr int b_off = kSmemAKBlocks * kABlockBytes;                // 163840
+  static constexpr int bar_off = b_off + kBStages * kBStageBytes;           // 221184
   // barriers (8 B each)
   static constexpr int full_bar = bar_off;                                  // [kBStages]
   static constexpr int empty_bar = full_bar + 8 * kBStages;                 // [kBStages]
@@ -288,8 +288,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         ptx::mbar_wait(a_empty_bar(kb), (my_item_no & 1) ^ 1, 150 + kb);
         ptx::tc_fence_after_sync();
-        ptx::tmem_st_32x16(tmem_base + lane_addr + a_tmem_col(0), r);            // k 0..31  -> columns above buffer 0
-        ptx::tmem_st_32x16(tmem_base + lane_addr + a_tmem_col(2), r + 16);       // k 32..63 -> columns above buffer 1
+        ptx::tmem_st_32x32(tmem_base + lane_addr + a_tmem_col(kb, 0), r);
         ptx::tmem_st_wait();
         ptx::tc_fence_before_sync();
         __syncwarp();
@@ -350,7 +349,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             for (int kk = 0; kk < 4; ++kk) {
               bd[kk] = ptx::make_kmajor_desc(b_addr + kk * 32, 128);
               ad[kk] = ptx::make_kmajor_desc(a_addr + kk * 32, 128);
-              at[kk] = tmem_base + a_tmem_col(kk);
+              at[kk] = tmem_base + a_tmem_col(a_in_tmem ? kb : 0, kk);
               asm volatile("" : "+l"(bd[kk]), "+l"(ad[kk]), "+r"(at[kk]));
             }
             if (kb == 0) { const long long c0 = prof ? clock64() : 0;
@@ -463,8 +462,8 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         ptx::tc_fence_after_sync();
         const long long tr0 = trace ? clock64() : 0;
         const uint32_t taddr = tmem_base + lane_addr + buf * kAccStride + half * kHalfCols;
-        // four 32-column chunks per half; the second half has 112 columns (its last chunk reads 16 columns of the
-        // TMEM-resident A operand, masked by n_valid)
+        // four 32-column chunks per half; the second half has only 96 columns (its fourth load reads the TMEM-resident
+        // A operand and is ignored: n_valid - 96 <= 0)
         uint32_t ra[32], rb[32];
         ptx::tmem_ld_32x32(taddr, ra);
         ptx::tmem_ld_wait(ra);                                   // ra = chunk 0
