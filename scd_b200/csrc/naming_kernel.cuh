@@ -6,19 +6,21 @@
 //   replaces  main_unsup.py:519-529 / main_ptsup.py:538-543 (GEMM -> [1024, V] logits in HBM ->
 //   softmax -> topk twice) and main_unsup.py:610-614 (k = 1 over the K selected columns).
 //
-// The N x V score matrix never exists: a CTA pair (cta_group::2, 256 x 192 x 16 tcgen05.mma) keeps its 256 image
-// rows stationary for a whole vocabulary sweep, streams the vocabulary through a deep TMA ring, accumulates each
-// 256 x 192 tile in TMEM (double buffered) and eight epilogue warps read the tile back with tcgen05.ld - one
+// The N x V score matrix never exists: a CTA pair (cta_group::2, 256 x 224 x 16 tcgen05.mma) keeps its 256 image
+// rows stationary for a whole vocabulary sweep, streams the vocabulary through a TMA ring, accumulates each
+// 256 x 224 tile in TMEM (double buffered) and eight epilogue warps read the tile back with tcgen05.ld - one
 // thread per image row.
 //
 // Operand placement is what the measurements forced (profiles/r1_name_cycle_counters.txt, r1_tma_feed.txt): a
 // vocabulary box needs ~600 cycles from L2 plus ~400 cycles of barrier round trips, so the ring must hold >= 3
 // k-blocks ahead of the tensor pipe; with all 192 KB of stationary rows in shared memory only 32 KB (2 k-blocks) were
-// left and the issuer spent 40 % of its time waiting for B (65 % tensor-active).  Now the first four 64-wide
+// left and the issuer spent 40 % of its time waiting for B (65 % tensor-active).  Now the first TWO 64-wide
 // k-blocks of the rows live in TENSOR MEMORY as the A operand (tcgen05.mma with A from TMEM; loader warps write them
-// with tcgen05.st, thread = row = TMEM lane), the other eight stay in shared memory (SWIZZLE_128B), and the 96 KB
-// that frees hold an 8-deep ring of 96-row x 64-k vocabulary boxes (12 KB, SWIZZLE_128B).  TMEM: accumulators at
-// columns [0,192) and [256,448), A k-blocks at [192,256) and [448,512).
+// with tcgen05.st, thread = row = TMEM lane), the other ten stay in shared memory (SWIZZLE_128B), and the 32 KB
+// that frees plus the old ring hold a 4-deep ring of 112-row x 64-k vocabulary boxes (14 KB per CTA, SWIZZLE_128B).
+// Wider tiles (224 instead of 192) amortise the fixed per-MMA issue cost over more columns - the tile sweep
+// (96 -> 192 -> 240 -> 224) measured 224 x 2 TMEM k-blocks x 4 stages fastest (2.76 ms on C2).
+// TMEM: accumulators at columns [0,224) and [256,480), A k-blocks at [224,256) and [480,512).
 //
 // The epilogue is a two-level selection: per 32-column chunk only the chunk maximum is computed (31 FMNMX) and
 // compared with the row's k-th best chunk maximum; the rare chunk that beats it is parked (32 floats) in an
@@ -26,9 +28,10 @@
 // exact scan of those k parked chunks at the end of the vocabulary sweep finishes the row.  (The unsupervised
 // driver's softmax additionally keeps a running max / sum-exp.)  Only [N, k] leaves the SM.
 //
-// Warp roles (512 threads): 0, 2 = vocabulary (B) TMA producers (alternate k-blocks; 2 also allocates TMEM),
-// 1, 3 = MMA issuers (leader CTA only, alternate k-blocks), 4..11 = epilogue (TMEM lane quadrant = warp & 3; warps
-// 4..7 take columns 0..95 of every accumulator tile, warps 8..11 columns 96..191), 12..15 = loaders of the
+// Warp roles (544 threads): 0, 2 = vocabulary (B) TMA producers (alternate k-blocks; 2 also allocates TMEM),
+// 1, 3, 16 = MMA issuers (leader CTA only, k-blocks round-robin, a shared-memory token keeps the issue order),
+// 4..11 = epilogue (TMEM lane quadrant = warp & 3; warps 4..7 take columns 0..127 of every accumulator tile,
+// warps 8..11 columns 128..223), 12..15 = loaders of the
 // TMEM-resident A k-blocks (global -> registers -> tcgen05.st); 12 is also the TMA producer of the shared-memory
 // A k-blocks.
 #pragma once
