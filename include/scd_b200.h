@@ -163,6 +163,21 @@ SCD_API int scd_label_histogram(const int64_t* labels, int64_t N, int K, int32_t
 SCD_API int scd_constrained_assign(const int32_t* cost, int64_t N, int K, int64_t size_min, int64_t size_max,
                            int32_t* labels, int64_t* total_cost /* nullable */, int64_t* n_augment /* nullable */);
 
+/* ---------------------------------------------------------------- evaluation either side of the path */
+
+/* gcd/project_utils/cluster_and_log_utils.py:45-49 (split_cluster_acc_v2: `for i in range(y_pred.size):
+ * w[y_pred[i], y_true[i]] += 1`) and the match counts of main_unsup.py:149-167 evaluate_semantic_acc:
+ * w [D,D] int64 (overwritten), row = predicted cluster, column = true class.  Either label vector may be int64 or
+ * float64 (the drivers' `targets` are float64, main_unsup.py:118,132; the reference casts with .astype(int)).
+ * first_row (nullable, [D] int64): first row index whose true class is t, N if the class never occurs (the order
+ * in which evaluate_semantic_acc's defaultdict meets the classes).  mask (nullable, [N] bytes, non-zero = set) with
+ * col_masked ([D] int64, overwritten): rows of true class t under the mask - :43-44's old/new class sets are the
+ * classes with col_masked > 0 / column sum - col_masked > 0.  *bad (device int32, caller zeroes) |= 1 when a label
+ * falls outside [0, D). */
+SCD_API int scd_contingency(const void* y_pred, int pred_is_f64, const void* y_true, int true_is_f64, int64_t N, int D,
+                    const uint8_t* mask /* nullable */, int64_t* w, int64_t* first_row /* nullable */,
+                    int64_t* col_masked /* nullable unless mask */, int32_t* bad, scd_stream_t stream);
+
 /* ---------------------------------------------------------------- host-side combinatorial step (a10) */
 
 /* gcd/project_utils/cluster_utils.py:234-275 linear_assignment (called from local_utils/clip_lang_util.py:178):

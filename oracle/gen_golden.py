@@ -342,17 +342,109 @@ def gen_naming(ref, lang):
     np.savez_compressed(os.path.join(OUT, 'naming_small.npz'), **res)
 
 
+# ------------------------------------------------------------------ evaluation + on-disk contract fixtures
+class _FakeImages:
+    """Stands in for an image batch: ``extract_feature`` only calls ``.cuda()`` on it and hands it to the model."""
+
+    def __init__(self, feats):
+        self.feats = feats
+
+    def cuda(self):
+        return self
+
+
+def gen_eval(ref):
+    """Runs the REAL ``split_cluster_acc_v2`` (imported), ``evaluate_semantic_acc`` and ``extract_feature`` (exec'd from
+    the source text of ``main_unsup.py``: the module itself does not import without matplotlib) on seeded inputs, and
+    writes the dicts the drivers ``torch.save`` (``main_unsup.py:294-300`` features, ``:366-371`` cluster result)."""
+    import importlib
+    from collections import defaultdict
+    clu = importlib.import_module('gcd.project_utils.cluster_and_log_utils')
+    unsup_src = os.path.join(ref, 'main_unsup.py')
+    sem_src, r1 = source_block(unsup_src, 'def evaluate_semantic_acc', 'return semantic_acc_avg, semantic_acc_all')
+    ext_src, r2 = source_block(unsup_src, 'def extract_feature', 'return data_dict')
+    ns = dict(defaultdict=defaultdict, np=np, torch=torch, tqdm=lambda x: x, print=lambda *a, **k: None)
+    exec(sem_src, ns)
+    exec(ext_src, ns)
+    res = dict(ranges=np.array([r1, r2]))
+    # (1) the reference's own known-answer case, gcd/notebooks/demo_acc_v2.ipynb
+    gt = np.array([0] * 5 + [1] * 5 + [2] * 5 + [3] * 5)
+    pr = np.array([2] * 4 + [0] * 1 + [1] * 4 + [3] * 1 + [0] * 4 + [3] * 1 + [3] * 5)
+    t, o, n_, m = clu.split_cluster_acc_v2(gt, pr, gt < 2, return_ind_map=True)
+    assert (t, o, n_, m) == (0.85, 0.8, 0.9, {2: 0, 1: 1, 0: 2, 3: 3}), (t, o, n_, m)
+    res.update(nb_gt=gt, nb_pred=pr, nb_acc=np.array([t, o, n_]), nb_map=np.array(sorted(m.items())))
+    # (2) seeded cases: float64 targets as the drivers pass them, more clusters than classes and vice versa, ties
+    rng = np.random.RandomState(41)
+    cases = [(400, 7, 7, 0.2), (1500, 12, 9, 0.35), (1500, 9, 14, 0.35), (64, 5, 5, 0.9), (3000, 40, 40, 0.1)]
+    for ci, (n, n_cls, n_clu, noise) in enumerate(cases):
+        y = rng.randint(0, n_cls, size=n)
+        perm = rng.permutation(max(n_cls, n_clu))
+        pred = np.where(rng.rand(n) < noise, rng.randint(0, n_clu, size=n), perm[y] % n_clu).astype(np.int64)
+        mask = y < n_cls // 2
+        y_f = y.astype(np.float64)
+        t, o, n_, m = clu.split_cluster_acc_v2(y_f, pred, mask, return_ind_map=True)
+        res[f'c{ci}_y'] = y_f
+        res[f'c{ci}_pred'] = pred
+        res[f'c{ci}_mask'] = mask
+        res[f'c{ci}_acc'] = np.array([t, o, n_], dtype=np.float64)
+        res[f'c{ci}_map'] = np.array(sorted(m.items()), dtype=np.int64)
+        # semantic accuracy: class c is called name 100 + c; cluster p was voted name 100 + (class it mostly holds),
+        # two clusters share a name and one name is unknown to every cluster
+        cidx_to_cname = {c: f'n{100 + c}' for c in range(n_cls)}
+        D = max(n_cls, n_clu)
+        w = np.zeros((D, D), dtype=int)
+        np.add.at(w, (pred, y), 1)
+        cand = [f'n{100 + int(w[p].argmax())}' for p in range(n_clu)]
+        cand[-1] = 'n_none'
+        for sub, sel in (('all', np.ones(n, bool)), ('old', mask), ('new', ~mask)):
+            a, b = ns['evaluate_semantic_acc'](y_f[sel], cidx_to_cname, pred[sel], cand)
+            res[f'c{ci}_sem_{sub}'] = np.array([a, b], dtype=np.float64)
+        res[f'c{ci}_cand'] = np.array(cand)
+        res[f'c{ci}_ncls'] = np.int64(n_cls)
+    np.savez_compressed(os.path.join(OUT, 'eval_small.npz'), **res)
+
+    # (3) on-disk contracts: the dict extract_feature returns (main_unsup.py:113-146) saved as the drivers do
+    # (:298), and the cluster-result dict (:366-371)
+    g = torch.Generator().manual_seed(51)
+    n, d = 300, 16
+    raw = torch.randn(n, d, generator=g)
+    labels = torch.randint(0, 8, (n,), generator=g)
+    lab_mask = (labels < 4) & (torch.rand(n, generator=g) < 0.5)
+    loader = [(_FakeImages(raw[i:i + 128]), labels[i:i + 128], None, lab_mask[i:i + 128]) for i in range(0, n, 128)]
+    args = _Args()
+    args.train_classes, args.feat_model = range(4), 'dino'
+    data_dict = ns['extract_feature'](lambda im: im.feats, loader, args)
+    torch.save(data_dict, os.path.join(OUT, 'features_all.pt'))
+    mask_lab = data_dict['mask_lab']
+    all_preds = rng.randint(0, 8, size=n)
+    cluster_result = {'all_preds': all_preds}
+    cluster_result['u_preds'] = all_preds[~mask_lab]
+    cluster_result['u_targets'] = data_dict['targets'][~mask_lab]
+    cluster_result['mask'] = data_dict['mask_cls'][~mask_lab].astype(bool)
+    torch.save(cluster_result, os.path.join(OUT, 'cluster_result.pt'))
+    np.savez_compressed(os.path.join(OUT, 'features_raw.npz'), raw=raw.numpy(), labels=labels.numpy(), lab_mask=lab_mask.numpy())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--ref', default='/root/reference')
+    ap.add_argument('--only', default=None, choices=[None, 'kmeans', 'constrained', 'hungarian', 'naming', 'eval'],
+                    help='regenerate one fixture family (the others are left as committed)')
     a = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)          # fixtures must not depend on the thread count of this box
     km_local, km_gcd, lang, cu = import_reference(a.ref)
-    gen_kmeans(km_local, km_gcd)
-    gen_constrained(a.ref)
-    gen_hungarian(cu)
-    gen_naming(a.ref, lang)
+    todo = lambda name: a.only in (None, name)
+    if todo('kmeans'):
+        gen_kmeans(km_local, km_gcd)
+    if todo('constrained'):
+        gen_constrained(a.ref)
+    if todo('hungarian'):
+        gen_hungarian(cu)
+    if todo('naming'):
+        gen_naming(a.ref, lang)
+    if todo('eval'):
+        gen_eval(a.ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -40,6 +40,7 @@ SIGNATURES = {
     'scd_vote_presorted': (_int, [_vp, _int, _int, _vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     'scd_label_histogram': (_int, [_vp, _i64, _int, _vp, _vp]),
     'scd_constrained_assign': (_int, [_vp, _i64, _int, _i64, _i64, _vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    'scd_contingency': (_int, [_vp, _int, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     'scd_linear_assignment': (_int, [_vp, _int, _int, _vp, C.POINTER(_int)]),
 }
 

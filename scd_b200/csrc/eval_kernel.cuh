@@ -4,7 +4,9 @@
 // as one pass over the two label vectors.  w is [D, D] int64, row = predicted cluster, column = true class.
 // `first_row[t]` = first row index whose true class is t (N when the class never occurs): the order in which
 // Python's defaultdict meets the class names (main_unsup.py:152), which fixes the float summation order of
-// semantic_acc_avg.
+// semantic_acc_avg.  `col_masked[t]` = number of rows of true class t with mask set: split_cluster_acc_v2's
+// old_classes_gt = set(y_true[mask]) / new_classes_gt = set(y_true[~mask]) (:43-44) are the classes with
+// col_masked > 0 / column sum - col_masked > 0.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -21,7 +23,8 @@ __device__ __forceinline__ long long as_label(T v) { return (long long)v; }
 template <typename TP, typename TT>
 __global__ void __launch_bounds__(256)
 contingency_kernel(const TP* __restrict__ y_pred, const TT* __restrict__ y_true, long long N, int D,
-                   unsigned long long* __restrict__ w, unsigned long long* __restrict__ first_row,
+                   const unsigned char* __restrict__ mask, unsigned long long* __restrict__ w,
+                   unsigned long long* __restrict__ first_row, unsigned long long* __restrict__ col_masked,
                    int* __restrict__ bad, int use_smem) {
   extern __shared__ int cont_sh[];
   const int cells = D * D;
@@ -36,6 +39,7 @@ contingency_kernel(const TP* __restrict__ y_pred, const TT* __restrict__ y_true,
     if (use_smem) atomicAdd(&cont_sh[(int)p * D + (int)t], 1);
     else atomicAdd(&w[p * D + t], 1ull);
     if (first_row) atomicMin(&first_row[t], (unsigned long long)i);
+    if (mask && mask[i]) atomicAdd(&col_masked[t], 1ull);
   }
   if (use_smem) {
     __syncthreads();

@@ -18,6 +18,7 @@
 #include "kmeans_kernel.cuh"
 #include "naming_kernel.cuh"
 #include "vote_kernel.cuh"
+#include "eval_kernel.cuh"
 
 namespace {
 
@@ -561,6 +562,37 @@ int scd_vote_presorted(const int64_t* topk_idx, int k_total, int k_used, const v
   const int* order = offsets + 2 * K + 1;
   return launch_vote(topk_idx, k_total, k_used, order, offsets, K, excluded, n_excluded, M, out_names, out_counts, out_distinct,
                      overflow, as_stream(stream));
+}
+
+int scd_contingency(const void* y_pred, int pred_is_f64, const void* y_true, int true_is_f64, int64_t N, int D,
+                    const uint8_t* mask, int64_t* w, int64_t* first_row, int64_t* col_masked, int32_t* bad, scd_stream_t stream) {
+  if (N < 0 || D <= 0 || D > 46340) return fail("scd_contingency: bad shape N=%lld D=%d", (long long)N, D);
+  if (!w || !bad || (N > 0 && (!y_pred || !y_true)) || (mask && !col_masked)) return fail("scd_contingency: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const long long cells = (long long)D * D;
+  SCD_CUDA(cudaMemsetAsync(w, 0, sizeof(int64_t) * (size_t)cells, st));
+  if (col_masked) SCD_CUDA(cudaMemsetAsync(col_masked, 0, sizeof(int64_t) * (size_t)D, st));
+  if (first_row) {
+    scd::fill_u64_kernel<<<(D + 255) / 256, 256, 0, st>>>(reinterpret_cast<unsigned long long*>(first_row), D, (unsigned long long)N);
+    SCD_LAUNCH_CHECK("fill_u64_kernel");
+  }
+  if (N == 0) return 0;
+  const int use_smem = cells <= scd::kContSmemCells ? 1 : 0;
+  const size_t smem = use_smem ? sizeof(int) * (size_t)cells : 0;
+  const int blocks = (int)std::min<long long>((N + 255) / 256, (long long)device_sm_count() * (use_smem ? 2 : 8));
+  auto* wp = reinterpret_cast<unsigned long long*>(w);
+  auto* fp = reinterpret_cast<unsigned long long*>(first_row);
+  auto* cm = reinterpret_cast<unsigned long long*>(col_masked);
+  if (!pred_is_f64 && !true_is_f64)
+    scd::contingency_kernel<long long, long long><<<blocks, 256, smem, st>>>(static_cast<const long long*>(y_pred), static_cast<const long long*>(y_true), N, D, mask, wp, fp, cm, bad, use_smem);
+  else if (!pred_is_f64 && true_is_f64)
+    scd::contingency_kernel<long long, double><<<blocks, 256, smem, st>>>(static_cast<const long long*>(y_pred), static_cast<const double*>(y_true), N, D, mask, wp, fp, cm, bad, use_smem);
+  else if (pred_is_f64 && !true_is_f64)
+    scd::contingency_kernel<double, long long><<<blocks, 256, smem, st>>>(static_cast<const double*>(y_pred), static_cast<const long long*>(y_true), N, D, mask, wp, fp, cm, bad, use_smem);
+  else
+    scd::contingency_kernel<double, double><<<blocks, 256, smem, st>>>(static_cast<const double*>(y_pred), static_cast<const double*>(y_true), N, D, mask, wp, fp, cm, bad, use_smem);
+  SCD_LAUNCH_CHECK("contingency_kernel");
+  return 0;
 }
 
 }  // extern "C"

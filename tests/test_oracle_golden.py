@@ -129,3 +129,33 @@ def test_ptsup_voting_loop(golden_dir):
         assert t['voted'] == g[f'ptsup_loop_voted_{r}'].tolist()
         assert t['cand'] == g[f'ptsup_loop_cand_{r}'].tolist()
         assert np.array_equal(t['u_preds'], g[f'ptsup_loop_preds_{r}'])
+
+
+# ------------------------------------------------------------------ evaluation metrics
+def _eval_cases(g):
+    for ci in range(5):
+        y, p, mask = g[f'c{ci}_y'], g[f'c{ci}_pred'], g[f'c{ci}_mask']
+        names = {c: f'n{100 + c}' for c in range(int(g[f'c{ci}_ncls']))}
+        yield ci, y, p, mask, names, [str(x) for x in g[f'c{ci}_cand']]
+
+
+def test_split_cluster_acc_v2_reproduces_the_notebook_known_answer(golden_dir):
+    """gcd/notebooks/demo_acc_v2.ipynb: 0.85 0.8 0.9 {2: 0, 1: 1, 0: 2, 3: 3} - the reference's one recorded answer"""
+    from oracle import eval_oracle
+    gt = np.array([0] * 5 + [1] * 5 + [2] * 5 + [3] * 5)
+    pr = np.array([2] * 4 + [0] * 1 + [1] * 4 + [3] * 1 + [0] * 4 + [3] * 1 + [3] * 5)
+    t, o, n, m = eval_oracle.split_cluster_acc_v2(gt, pr, gt < 2, return_ind_map=True)
+    assert (t, o, n) == (0.85, 0.8, 0.9) and {int(k): int(v) for k, v in m.items()} == {2: 0, 1: 1, 0: 2, 3: 3}
+    g = _load(golden_dir, 'eval_small.npz')
+    assert np.array_equal(g['nb_acc'], [0.85, 0.8, 0.9])
+
+
+def test_eval_oracle_matches_reference(golden_dir):
+    from oracle import eval_oracle
+    g = _load(golden_dir, 'eval_small.npz')
+    for ci, y, p, mask, names, cand in _eval_cases(g):
+        t, o, n, m = eval_oracle.split_cluster_acc_v2(y, p, mask, return_ind_map=True)
+        assert np.array_equal(np.array([t, o, n]), g[f'c{ci}_acc'])                      # float64, bit-exact
+        assert np.array_equal(np.array(sorted(m.items())), g[f'c{ci}_map'])
+        for sub, sel in (('all', np.ones(len(y), bool)), ('old', mask), ('new', ~mask)):
+            assert np.array_equal(np.array(eval_oracle.evaluate_semantic_acc(y[sel], names, p[sel], cand)), g[f'c{ci}_sem_{sub}'])
