@@ -10,17 +10,25 @@
 // which measures 3.8e-7 max abs error on unit-norm data (the fp32 direct form: 2.6e-7).
 //
 // X stays fp32 in HBM and is read exactly ONCE per E-step: TMA brings 128 x 32 fp32 tiles into a ring,
-// four converter warps (thread = row) split them into the hi / lo bf16 K-major operand tiles in shared
-// memory (SWIZZLE_64B layout written by hand, fence.proxy.async, mbarrier hand-off to the MMA warp) and
-// accumulate ||x||^2 on the way.  The centroid hi / lo planes (+ ||c||^2) are prepared per iteration by a
-// tiny kernel and streamed from L2.  Accumulators live in TMEM (2 x 256 columns, double buffered); the
+// four converter warps (thread = row) split them into the hi / lo bf16 A operand and accumulate ||x||^2 on
+// the way.  Where the converted operand goes is the template parameter:
+//   kTmemA = true  (n_tile <= 160, i.e. K <= 160): into TENSOR MEMORY (tcgen05.st, thread = row = TMEM lane, one 32-bit
+//       column = two consecutive k), in the columns the double-buffered accumulators leave free, and the MMAs take A
+//       from TMEM.  Per 32-wide k-block this removes 16 KB of converter stores and 24 KB of MMA operand reads from
+//       shared memory - the round-1 kernel moved 107 KB per k-block through shared memory (~840 cycles at 128 B/clk
+//       against ~340 cycles of tensor work) and sat at 0.5 of the HBM roofline, shared-memory-bandwidth bound
+//       (profiles/r1_estep_cycle_counters.txt) - and the 48 KB of the old A ring become three more X stages in flight.
+//   kTmemA = false (wider centroid tiles, no free TMEM columns): K-major operand tiles in shared memory (SWIZZLE_64B
+//       layout written by hand, fence.proxy.async, mbarrier hand-off to the MMA warp).
+// The centroid hi / lo planes (+ ||c||^2) are prepared per iteration by a tiny kernel and streamed from L2.  Accumulators live in TMEM (2 x 256 columns, double buffered); the
 // epilogue warps (thread = row) fold  ||c||^2 - 2 acc  into a running argmin, so [N, K] never exists.
 // HBM-bound while 3 * K <~ 500 (K = 100 / 120 / 200); tensor-bound for K = 1000.
 //
-// Warp roles (512 threads, 1 CTA / SM, persistent over 128-row tiles):
-//   0, 3 X TMA producers (alternate k-blocks) | 1 MMA issuer | 2 TMEM allocator, then centroid TMA producer (hi + lo
-//   planes as one 3-D box) | 4-11 converters (two sets of four warps that take alternate k-blocks, so every scheduler
-//   has two conversions in flight) | 12-15 epilogue
+// Warp roles (608 threads, 1 CTA / SM, persistent over 128-row tiles):
+//   0, 3 X TMA producers (alternate k-blocks) | 1, 16, 17 MMA issuers (k-blocks round-robin, named-barrier token) |
+//   2 (also the TMEM allocator), 18 centroid TMA producers (alternate k-blocks; hi + lo planes as one 3-D box) |
+//   4-11 converters (two sets of four warps that take alternate k-blocks, so every scheduler has two conversions in
+//   flight) | 12-15 epilogue
 #pragma once
 #include "ptx.cuh"
 #include <cuda_bf16.h>
@@ -30,27 +38,32 @@ namespace scd {
 constexpr int kEsBM = 128;              // rows per tile
 constexpr int kEsBK = 32;               // k per stage
 constexpr int kEsMaxXStages = 12;       // fp32 X ring: as deep as shared memory allows (host picks EsParams::x_stages)
-constexpr int kEsAStages = 3;           // converted hi/lo ring
+constexpr int kEsAStages = 3;           // converted hi/lo ring in shared memory (kTmemA = false)
+constexpr int kEsMaxAStages = 8;        // ... in tensor memory (kTmemA = true): 32 columns per stage, up to 4 above each accumulator
 constexpr int kEsBStages = 3;           // centroid hi/lo ring
 constexpr int kEsXBytes = kEsBM * kEsBK * 4;          // 16384
 constexpr int kEsAPlane = kEsBM * kEsBK * 2;          // 8192 (one of hi / lo)
 constexpr int kEsConvSets = 2;          // converter warp sets (4 warps each), alternating k-blocks
-constexpr int kEsThreads = 32 * (4 + 4 * kEsConvSets + 4);
+constexpr int kEsIssuers = 3;           // MMA issuer warps (1, 16, 17), k-blocks round-robin
+constexpr int kEsFirstExtraIssuer = 4 + 4 * kEsConvSets + 4;       // warps 16, 17
+constexpr int kEsSecondCProducer = kEsFirstExtraIssuer + kEsIssuers - 1;   // warp 18
+constexpr int kEsThreads = 32 * (kEsSecondCProducer + 1);
 constexpr int kEsMaxK = 1024;
 
-// Dynamic shared memory: [X ring: x_stages x 16 KB][A ring: 3 x (hi, lo) x 8 KB][B ring: 3 x (hi, lo) x b_plane]
+// Dynamic shared memory: [X ring: x_stages x 16 KB][A ring: 3 x (hi, lo) x 8 KB, kTmemA = false only][B ring: 3 x (hi, lo) x b_plane]
 // [tail: barriers, TMEM pointer, ||c||^2, ||x||^2 ring].  The E-step is HBM-latency bound (ncu, round 1: the
 // converters wait on x_full), so whatever the centroid ring does not need goes to X stages in flight.
 struct EsTail {
   static constexpr int x_full = 0;                                              // [12]
   static constexpr int x_empty = x_full + 8 * kEsMaxXStages;
-  static constexpr int a_full = x_empty + 8 * kEsMaxXStages;                    // [3]
-  static constexpr int a_empty = a_full + 8 * kEsAStages;
-  static constexpr int b_full = a_empty + 8 * kEsAStages;                       // [3]
+  static constexpr int a_full = x_empty + 8 * kEsMaxXStages;                    // [8]
+  static constexpr int a_empty = a_full + 8 * kEsMaxAStages;
+  static constexpr int b_full = a_empty + 8 * kEsMaxAStages;                    // [3]
   static constexpr int b_empty = b_full + 8 * kEsBStages;
   static constexpr int t_full = b_empty + 8 * kEsBStages;                       // [2]
   static constexpr int t_empty = t_full + 16;
-  static constexpr int tmem_ptr = t_empty + 16;
+  static constexpr int drain = t_empty + 16;                                    // every issuer's last commit has landed
+  static constexpr int tmem_ptr = drain + 16;
   static constexpr int cnorm = tmem_ptr + 16;                                   // [kEsMaxK] floats
   static constexpr int xnorm = cnorm + 4 * kEsMaxK;                             // [4 tiles][sets][128] floats
   static constexpr int total = xnorm + 4 * 4 * kEsConvSets * kEsBM;
@@ -66,6 +79,8 @@ struct EsParams {
   int n_row_tiles;
   int x_stages;            // depth of the fp32 X ring (2 .. kEsMaxXStages)
   int b_plane;             // bytes of one centroid plane stage: n_tile * 64 (n_tile % 16 == 0, so a multiple of 1024)
+  int a_stages;            // depth of the converted-operand ring: kEsAStages = 3 (shared memory) or 6 (TMEM) - a multiple of
+                           // the issuer count; never more than 2 * num_kb, so the 4-deep ||x||^2 ring cannot be overrun
   const float* cnorm;      // [K]
   long long* labels;       // [N]
   float* mindist;          // nullable [N]
@@ -76,10 +91,10 @@ struct EsParams {
 // host + device: byte offsets of the rings for a given plan
 struct EsLayout {
   int x_off, a_off, b_off, tail_off, total;
-  __host__ __device__ EsLayout(int x_stages, int b_plane) {
+  __host__ __device__ EsLayout(int x_stages, int b_plane, bool tmem_a) {
     x_off = 0;
     a_off = x_off + x_stages * kEsXBytes;
-    b_off = a_off + kEsAStages * 2 * kEsAPlane;
+    b_off = a_off + (tmem_a ? 0 : kEsAStages * 2 * kEsAPlane);
     tail_off = b_off + kEsBStages * 2 * b_plane;
     total = tail_off + EsTail::total;
   }
@@ -110,10 +125,21 @@ __global__ void centroid_split_kernel(const float* __restrict__ C, int K, int D,
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ float fmin_nan(float a, float b) {        // NaN if either input is NaN
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
 __device__ __forceinline__ bool es_better(float cand, float cur) {
   return (cand < cur) || (cand != cand && cur == cur);      // torch.min: strict '<', a NaN beats any number
 }
 
+// TMEM column of A stage s (kTmemA): stages alternate between the free columns above accumulator 0 and accumulator 1;
+// hi plane = 16 columns (32 k), lo plane = the next 16
+__device__ __forceinline__ uint32_t es_a_col(int s, int n_tile) { return (uint32_t)((s & 1) * 256 + n_tile + (s >> 1) * 32); }
+
+template <bool kTmemA>
 __global__ void __launch_bounds__(kEsThreads, 1)
 estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c, const EsParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -122,8 +148,9 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
   const int nkb = p.num_kb;
-  const EsLayout L(p.x_stages, p.b_plane);
+  const EsLayout L(p.x_stages, p.b_plane, kTmemA);
   const int kEsXStages = p.x_stages;
+  const int n_as = p.a_stages;
 
   auto bar = [&](int base, int i) { return sbase + L.tail_off + base + 8 * i; };
   const bool prof = p.prof != nullptr;
@@ -141,9 +168,10 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kEsXStages; ++s) { ptx::mbar_init(bar(EsTail::x_full, s), 1); ptx::mbar_init(bar(EsTail::x_empty, s), 4); }
-    for (int s = 0; s < kEsAStages; ++s) { ptx::mbar_init(bar(EsTail::a_full, s), 4); ptx::mbar_init(bar(EsTail::a_empty, s), 1); }
+    for (int s = 0; s < n_as; ++s) { ptx::mbar_init(bar(EsTail::a_full, s), 4); ptx::mbar_init(bar(EsTail::a_empty, s), 1); }
     for (int s = 0; s < kEsBStages; ++s) { ptx::mbar_init(bar(EsTail::b_full, s), 1); ptx::mbar_init(bar(EsTail::b_empty, s), 1); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(bar(EsTail::t_full, b), 1); ptx::mbar_init(bar(EsTail::t_empty, b), 4); }
+    ptx::mbar_init(bar(EsTail::drain, 0), kEsIssuers);
     ptx::fence_mbar_init_cluster();
   }
   if (warp == 2) {
@@ -183,15 +211,19 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       }
       if (prof && warp == 0) { pf[0] = clock64() - t0; pf[1] = w_xe; }
     }
-  } else if (warp == 2) {
-    // =================================================== centroid TMA producer: hi + lo planes in ONE 3-D box
+  } else if (warp == 2 || warp == kEsSecondCProducer) {
+    // =================================================== centroid TMA producers: hi + lo planes in ONE 3-D box
+    // (warp 2: even k-blocks, warp 18: odd - one warp gets one box out of L2 every ~500-600 cycles, which is the
+    // whole k-block budget once the MMAs run at the tensor pipe's rate)
     if (lane == 0) {
+      const uint32_t me = warp == 2 ? 0u : 1u;
       const uint32_t b_bytes = 2u * (uint32_t)p.n_tile * kEsBK * 2u;
       uint32_t g = 0;
       long long w_be = 0;
       for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x) {
         for (int nt = 0; nt < p.n_ntiles; ++nt) {
           for (int kb = 0; kb < nkb; ++kb, ++g) {
+            if ((g & 1u) != me) continue;
             const uint32_t bs = g % kEsBStages, bph = (g / kEsBStages) & 1u;
             twait(bar(EsTail::b_empty, bs), bph ^ 1, 710 + bs, w_be);
             ptx::mbar_arrive_expect_tx(bar(EsTail::b_full, bs), b_bytes);
@@ -200,45 +232,109 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           }
         }
       }
-      if (prof) pf[2] = w_be;
+      if (prof && warp == 2) pf[2] = w_be;
     }
-  } else if (warp == 1) {
-    // =================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16_f32(kEsBM, (uint32_t)p.n_tile);
-      int as = 0, bs = 0; uint32_t aph = 0, bph = 0, tile_no = 0;
-      long long w_te = 0, w_af = 0, w_bf = 0; const long long t0 = prof ? clock64() : 0;
-      for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x) {
-        for (int nt = 0; nt < p.n_ntiles; ++nt, ++tile_no) {
-          const uint32_t buf = tile_no & 1u;
-          twait(bar(EsTail::t_empty, buf), ((tile_no >> 1) & 1u) ^ 1u, 720 + buf, w_te);
-          ptx::tc_fence_after_sync();
-          const uint32_t d_tmem = tmem_base + buf * 256;
-          for (int kb = 0; kb < nkb; ++kb) {
-            twait(bar(EsTail::a_full, as), aph, 730 + as, w_af);
-            twait(bar(EsTail::b_full, bs), bph, 740 + bs, w_bf);
-            ptx::tc_fence_after_sync();
-            const uint32_t a_hi = sbase + L.a_off + as * 2 * kEsAPlane, a_lo = a_hi + kEsAPlane;
-            const uint32_t b_hi = sbase + L.b_off + bs * 2 * p.b_plane, b_lo = b_hi + p.b_plane;
+  } else if (warp == 1 || (warp >= kEsFirstExtraIssuer && warp < kEsFirstExtraIssuer + kEsIssuers - 1)) {
+    // =================================================== MMA issuers (warps 1, 16, 17), k-blocks round-robin
+    // tools/mma_rate_bench.cu: the pipe runs a 128 x N x 16 MMA in N/2 cycles only when the next one is already queued;
+    // an issuer that recomputes its descriptors between MMAs pays a ~96-cycle floor per MMA (N = 112: 56 ideal), because
+    // tcgen05.mma keeps the uniform registers of its descriptors busy until it has run.  With ONE issuing thread this
+    // kernel spent ~150 cycles per MMA, ~900 per k-block against a 710-cycle HBM budget (profiles/r1_estep_cycle_
+    // counters.txt; moving A into TMEM did not change that).  So, as in the naming kernel, three warps take the k-blocks
+    // round-robin: each prepares its six MMAs' operands and does its barrier waits while the other two warps' MMAs run,
+    // waits for a named-barrier token (ids 1..3), fires its MMAs back to back and hands the token on before committing.
+    // The token keeps the issue order = the pipe's execution order, so the last k-block's commit covers the whole tile.
+    // Issuer `me` owns k-blocks g = me, me + 3, ...: with 3 centroid stages and 3 (or 6) A stages its centroid stage is
+    // always `me` and its A stage is `me` (or alternates me, me + 3), so every descriptor is LOOP INVARIANT and can stay
+    // in uniform registers for the whole kernel (the rate the micro-benchmark reaches with invariant descriptors).
+    static_assert(kEsIssuers == kEsBStages, "an issuer's centroid stage must be constant");
+    constexpr int kASets = kTmemA ? 2 : 1;                       // A stages per issuer (a_stages = 3 * kASets)
+    const uint32_t me = warp == 1 ? 0u : warp - kEsFirstExtraIssuer + 1u;
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(kEsBM, (uint32_t)p.n_tile);
+    const uint32_t bs = me;
+    const uint32_t b_hi = sbase + L.b_off + bs * 2 * p.b_plane, b_lo = b_hi + p.b_plane;
+    uint64_t dbh[2], dbl[2], dah[kASets][2], dal[kASets][2];
+    uint32_t ath[kASets][2], atl[kASets][2];
 #pragma unroll
-            for (int kk = 0; kk < kEsBK / 16; ++kk) {
-              const uint32_t ko = kk * 32;          // 16 bf16 = 32 bytes inside the 64-byte swizzle atom
-              const uint64_t dah = ptx::make_kmajor_desc(a_hi + ko, 64), dal = ptx::make_kmajor_desc(a_lo + ko, 64);
-              const uint64_t dbh = ptx::make_kmajor_desc(b_hi + ko, 64), dbl = ptx::make_kmajor_desc(b_lo + ko, 64);
-              ptx::umma_bf16<1>(d_tmem, dah, dbh, idesc, (kb | kk) != 0 ? 1u : 0u);
-              ptx::umma_bf16<1>(d_tmem, dah, dbl, idesc, 1u);
-              ptx::umma_bf16<1>(d_tmem, dal, dbh, idesc, 1u);
-            }
-            ptx::umma_commit<1>(bar(EsTail::a_empty, as), 0);
-            ptx::umma_commit<1>(bar(EsTail::b_empty, bs), 0);
-            if (++as == kEsAStages) { as = 0; aph ^= 1; }
-            if (++bs == kEsBStages) { bs = 0; bph ^= 1; }
-          }
-          ptx::umma_commit<1>(bar(EsTail::t_full, buf), 0);
+    for (int kk = 0; kk < kEsBK / 16; ++kk) {
+      const uint32_t ko = kk * 32;                               // 16 bf16 = 32 bytes inside the 64-byte swizzle atom
+      dbh[kk] = ptx::make_kmajor_desc(b_hi + ko, 64);
+      dbl[kk] = ptx::make_kmajor_desc(b_lo + ko, 64);
+#pragma unroll
+      for (int u = 0; u < kASets; ++u) {
+        const int as = (int)me + 3 * u;
+        if constexpr (kTmemA) {
+          ath[u][kk] = tmem_base + es_a_col(as, p.n_tile) + kk * 8;       // hi: columns +0..15, lo: +16..31
+          atl[u][kk] = ath[u][kk] + 16;
+          dah[u][kk] = dal[u][kk] = 0;
+        } else {
+          const uint32_t a_hi = sbase + L.a_off + as * 2 * kEsAPlane;
+          dah[u][kk] = ptx::make_kmajor_desc(a_hi + ko, 64);
+          dal[u][kk] = ptx::make_kmajor_desc(a_hi + kEsAPlane + ko, 64);
+          ath[u][kk] = atl[u][kk] = 0;
         }
       }
-      if (prof) { pf[3] = clock64() - t0; pf[4] = w_te; pf[5] = w_af; pf[6] = w_bf; pf[11] = tile_no; }
     }
+    const uint32_t my_tiles = blockIdx.x < (uint32_t)p.n_row_tiles ? ((uint32_t)p.n_row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    const uint32_t g_total = my_tiles * (uint32_t)p.n_ntiles * (uint32_t)nkb;
+    const bool iprof = prof && me == 0;
+    long long w_te = 0, w_af = 0, w_bf = 0, w_tok = 0; const long long t0 = iprof ? clock64() : 0;
+    uint32_t kb = me % (uint32_t)nkb, tile_no = me / (uint32_t)nkb;      // of k-block g, advanced by 3 per step
+    for (uint32_t g0 = me; g0 < g_total; g0 += kEsIssuers * kASets) {
+#pragma unroll
+      for (int u = 0; u < kASets; ++u) {
+        const uint32_t g = g0 + kEsIssuers * u;
+        if (g >= g_total) break;
+        const uint32_t as = me + 3u * (uint32_t)u;
+        const uint32_t aph = (g / (uint32_t)(kEsIssuers * kASets)) & 1u, bph = (g / kEsBStages) & 1u;
+        const uint32_t buf = tile_no & 1u;
+        const uint32_t d_tmem = tmem_base + buf * 256;
+        if (kb == 0) {
+          if (iprof) twait(bar(EsTail::t_empty, buf), ((tile_no >> 1) & 1u) ^ 1u, 720 + buf, w_te);
+          else ptx::mbar_wait(bar(EsTail::t_empty, buf), ((tile_no >> 1) & 1u) ^ 1u, 720 + buf);
+        }
+        if (iprof) { twait(bar(EsTail::a_full, as), aph, 730 + as, w_af); twait(bar(EsTail::b_full, bs), bph, 740 + bs, w_bf); }
+        else { ptx::mbar_wait(bar(EsTail::a_full, as), aph, 730 + as); ptx::mbar_wait(bar(EsTail::b_full, bs), bph, 740 + bs); }
+        ptx::tc_fence_after_sync();
+        if (g > 0) {                                                   // token: the previous issuer has issued k-block g - 1
+          const long long c0 = iprof ? clock64() : 0;
+          ptx::named_bar_sync(1 + me, 64);
+          if (iprof) w_tok += clock64() - c0;
+        }
+        const bool elected = ptx::elect_one();
+        if (elected) {
+#pragma unroll
+          for (int kk = 0; kk < kEsBK / 16; ++kk) {
+            if constexpr (kTmemA) {
+              ptx::umma_bf16_ts<1>(d_tmem, ath[u][kk], dbh[kk], idesc, (kb | (uint32_t)kk) != 0 ? 1u : 0u);
+              ptx::umma_bf16_ts<1>(d_tmem, ath[u][kk], dbl[kk], idesc, 1u);
+              ptx::umma_bf16_ts<1>(d_tmem, atl[u][kk], dbh[kk], idesc, 1u);
+            } else {
+              ptx::umma_bf16<1>(d_tmem, dah[u][kk], dbh[kk], idesc, (kb | (uint32_t)kk) != 0 ? 1u : 0u);
+              ptx::umma_bf16<1>(d_tmem, dah[u][kk], dbl[kk], idesc, 1u);
+              ptx::umma_bf16<1>(d_tmem, dal[u][kk], dbh[kk], idesc, 1u);
+            }
+          }
+        }
+        __syncwarp();
+        if (g + 1 < g_total) ptx::named_bar_arrive(1 + (me + 1) % kEsIssuers, 64);      // hand the token over ...
+        if (elected) {                                                                  // ... then commit
+          ptx::umma_commit<1>(bar(EsTail::a_empty, as), 0);
+          ptx::umma_commit<1>(bar(EsTail::b_empty, bs), 0);
+          if (kb == (uint32_t)nkb - 1) ptx::umma_commit<1>(bar(EsTail::t_full, buf), 0);
+        }
+        __syncwarp();
+        kb += kEsIssuers;
+        while (kb >= (uint32_t)nkb) { kb -= (uint32_t)nkb; ++tile_no; }
+      }
+    }
+    // No tcgen05.commit of this CTA may still be in flight when it exits (its mbarrier arrive would land in shared
+    // memory that no longer belongs to it): commits of one thread complete in order, so one more per issuer on a
+    // drain barrier, awaited by all issuers, covers the a_empty / b_empty commits nobody waits for at the end.
+    if (ptx::elect_one()) ptx::umma_commit<1>(bar(EsTail::drain, 0), 0);
+    __syncwarp();
+    ptx::mbar_wait(bar(EsTail::drain, 0), 0, 790);
+    if (iprof && lane == 0) { pf[3] = clock64() - t0; pf[4] = w_te; pf[5] = w_af; pf[6] = w_bf; pf[11] = tile_no; pf[12] = w_tok; }
   } else if (warp >= 4 && warp < 4 + 4 * kEsConvSets) {
     // =================================================== converters: fp32 tile -> bf16 hi / lo operand tiles
     // Set `cset` handles the k-blocks whose running index g (over the whole kernel) is congruent to cset.
@@ -246,17 +342,31 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const int row = (int)((warp - 4) & 3) * 32 + (int)lane;
     const uint32_t x_row = (uint32_t)row * 128u, x_sw = (uint32_t)(row & 7);
     const uint32_t a_row = (uint32_t)row * 64u, a_sw = (uint32_t)((row >> 1) & 3);
+    const uint32_t a_lane = (((warp & 3u) * 32u) << 16);       // this warp's TMEM lane quadrant (row = quadrant * 32 + lane)
     float* xnorm_s = reinterpret_cast<float*>(smem + L.tail_off + EsTail::xnorm);
     uint32_t g = 0;                       // running k-block index: ring slots and parities derive from it
     uint32_t my_tile = 0;                 // row tiles this CTA has converted: ||x||^2 slot = my_tile & 3
     long long w_xf = 0, w_ae = 0; const long long t0c = prof ? clock64() : 0;
+    int pend_as = -1;                     // kTmemA: A stage whose tcgen05.st are in flight and not yet published
+    auto publish_pending = [&]() {
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(EsTail::a_full, (uint32_t)pend_as));
+      pend_as = -1;
+    };
+    // ring slots / parities of this set's k-blocks advance incrementally (g steps by kEsConvSets): the runtime
+    // divisions by x_stages / a_stages cost ~40 dependent instructions per k-block (ncu source view)
+    uint32_t xs = (uint32_t)cset % (uint32_t)kEsXStages, xph = ((uint32_t)cset / (uint32_t)kEsXStages) & 1u;
+    uint32_t as = (uint32_t)cset % (uint32_t)n_as, aph = ((uint32_t)cset / (uint32_t)n_as) & 1u;
     for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x, ++my_tile) {
-      for (int nt = 0; nt < p.n_ntiles; ++nt) {
-        float norm = 0.f;
-        for (int kb = 0; kb < nkb; ++kb, ++g) {
-          if ((int)(g % kEsConvSets) != cset) continue;
-          const uint32_t xs = g % kEsXStages, xph = (g / kEsXStages) & 1u;
-          const uint32_t as = g % kEsAStages, aph = (g / kEsAStages) & 1u;
+      for (int nt = 0; nt < p.n_ntiles; ++nt, g += (uint32_t)nkb) {
+        float2 norm2 = make_float2(0.f, 0.f);
+        // g = running index of this tile's k-block 0; this set owns the k-blocks with (g + kb) % kEsConvSets == cset
+        for (int kb = (int)(((uint32_t)cset + kEsConvSets - g % kEsConvSets) % kEsConvSets); kb < nkb; kb += kEsConvSets) {
+          // the previous k-block's TMEM stores are published only once this k-block's X tile is in registers (their
+          // latency hides behind the wait and the loads) - unless that tile is not there yet
+          if (pend_as >= 0 && !__all_sync(0xffffffffu, ptx::mbar_test_wait(bar(EsTail::x_full, xs), xph))) publish_pending();
           twait(bar(EsTail::x_full, xs), xph, 750 + xs, w_xf);
           const uint8_t* xt = smem + L.x_off + xs * kEsXBytes + x_row;
           float4 f[8];
@@ -264,42 +374,56 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           for (int j = 0; j < 8; ++j) f[j] = *reinterpret_cast<const float4*>(xt + ((((uint32_t)j) ^ x_sw) << 4));
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(bar(EsTail::x_empty, xs));      // the fp32 stage is in registers
+          if (pend_as >= 0) publish_pending();
           uint4 hi[4], lo[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const float v[8] = {f[2 * c].x, f[2 * c].y, f[2 * c].z, f[2 * c].w, f[2 * c + 1].x, f[2 * c + 1].y, f[2 * c + 1].z, f[2 * c + 1].w};
+            const float2 v[4] = {make_float2(f[2 * c].x, f[2 * c].y), make_float2(f[2 * c].z, f[2 * c].w),
+                                 make_float2(f[2 * c + 1].x, f[2 * c + 1].y), make_float2(f[2 * c + 1].z, f[2 * c + 1].w)};
             uint32_t h[4], l[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-              const float r0 = v[2 * q] - __bfloat162float(hh.x), r1 = v[2 * q + 1] - __bfloat162float(hh.y);
-              const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(v[q].x, v[q].y);
               h[q] = *reinterpret_cast<const uint32_t*>(&hh);
+              // residual x - x_hi (exact in fp32) and ||x||^2, two lanes per instruction (fma.rn.f32x2)
+              const float2 hf = make_float2(__uint_as_float(h[q] << 16), __uint_as_float(h[q] & 0xffff0000u));
+              const float2 r = __ffma2_rn(hf, make_float2(-1.f, -1.f), v[q]);
+              const __nv_bfloat162 ll = __floats2bfloat162_rn(r.x, r.y);
               l[q] = *reinterpret_cast<const uint32_t*>(&ll);
-              norm = fmaf(v[2 * q], v[2 * q], norm);
-              norm = fmaf(v[2 * q + 1], v[2 * q + 1], norm);
+              norm2 = __ffma2_rn(v[q], v[q], norm2);
             }
             hi[c] = make_uint4(h[0], h[1], h[2], h[3]);
             lo[c] = make_uint4(l[0], l[1], l[2], l[3]);
           }
           twait(bar(EsTail::a_empty, as), aph ^ 1, 760 + as, w_ae);
-          uint8_t* at = smem + L.a_off + as * 2 * kEsAPlane + a_row;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t off = (((uint32_t)c) ^ a_sw) << 4;
-            *reinterpret_cast<uint4*>(at + off) = hi[c];
-            *reinterpret_cast<uint4*>(at + kEsAPlane + off) = lo[c];
-          }
           // this set's last k-block of the tile: publish its share of ||x||^2 before the a_full arrive
-          if (nt == 0 && kb + kEsConvSets >= nkb) xnorm_s[((my_tile & 3u) * kEsConvSets + cset) * kEsBM + row] = norm;
-          fence_proxy_async_smem();                                       // generic-proxy writes -> visible to the tensor core
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar(EsTail::a_full, as));
+          if (nt == 0 && kb + kEsConvSets >= nkb) xnorm_s[((my_tile & 3u) * kEsConvSets + cset) * kEsBM + row] = norm2.x + norm2.y;
+          if constexpr (kTmemA) {
+            ptx::tc_fence_after_sync();                                   // the MMAs that read this stage have completed
+            const uint32_t a_t = tmem_base + a_lane + es_a_col((int)as, p.n_tile);
+            ptx::tmem_st_32x16(a_t, reinterpret_cast<const uint32_t*>(hi));
+            ptx::tmem_st_32x16(a_t + 16, reinterpret_cast<const uint32_t*>(lo));
+            pend_as = (int)as;                                            // wait::st + a_full arrive: publish_pending()
+          } else {
+            uint8_t* at = smem + L.a_off + as * 2 * kEsAPlane + a_row;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t off = (((uint32_t)c) ^ a_sw) << 4;
+              *reinterpret_cast<uint4*>(at + off) = hi[c];
+              *reinterpret_cast<uint4*>(at + kEsAPlane + off) = lo[c];
+            }
+            fence_proxy_async_smem();                                     // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar(EsTail::a_full, as));
+          }
+          xs += kEsConvSets; if (xs >= (uint32_t)kEsXStages) { xs -= (uint32_t)kEsXStages; xph ^= 1u; }
+          as += kEsConvSets; if (as >= (uint32_t)n_as) { as -= (uint32_t)n_as; aph ^= 1u; }
         }
       }
     }
+    if (pend_as >= 0) publish_pending();
     if (prof && warp == 4 && lane == 0) { pf[7] = clock64() - t0c; pf[8] = w_xf; pf[9] = w_ae; }
-  } else if (warp >= 4 + 4 * kEsConvSets) {
+  } else if (warp >= 4 + 4 * kEsConvSets && warp < 4 + 4 * kEsConvSets + 4) {
     // =================================================== epilogue: running argmin per row
     const uint32_t quad = warp & 3u;
     const int row_in_tile = (int)quad * 32 + (int)lane;
@@ -309,8 +433,8 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     uint32_t tile_no = 0, my_tile = 0;
     double inertia_local = 0.0;
     long long w_tf = 0;
-    // the converters run at most 2 accumulator tiles + 3 operand stages ahead of this warp, so the
-    // 4-deep ||x||^2 ring (slot = row tiles done & 3) is never overwritten before it is read
+    // the converters run at most 2 accumulator tiles + a_stages <= 2 * num_kb operand stages (two tiles) ahead of
+    // this warp, so the 4-deep ||x||^2 ring (slot = row tiles done & 3) is never overwritten before it is read
     for (int rt = blockIdx.x; rt < p.n_row_tiles; rt += gridDim.x, ++my_tile) {
       float best = INFINITY; int best_k = -1;
       float xn = 0.f;
@@ -326,16 +450,47 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const int k0 = nt * 256;
         const int n_here = min(p.n_clusters - k0, 256);
 #pragma unroll 1
-        for (int c = 0; c * 32 < p.n_tile; ++c) {
+        for (int c = 0; c * 32 < n_here; ++c) {
           uint32_t r[32];
-          ptx::tmem_ld_32x32(taddr + c * 32, r);     // columns past n_tile are stale TMEM, masked below
+          ptx::tmem_ld_32x32(taddr + c * 32, r);     // columns past n_here are zero-padded centroids or stale TMEM, masked below
           ptx::tmem_ld_wait(r);
+          const int kbase = k0 + c * 32;
+          const int n_valid = min(n_here - c * 32, 32);
+          float d[32];
+          const float4* cn4 = reinterpret_cast<const float4*>(cn + kbase);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int kk = c * 32 + j;
-            if (kk < n_here) {
-              const float d = fmaf(-2.f, __uint_as_float(r[j]), cn[k0 + kk]);
-              if (best_k < 0 || es_better(d, best)) { best = d; best_k = k0 + kk; }
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 c4 = cn4[j4];
+            d[4 * j4 + 0] = fmaf(-2.f, __uint_as_float(r[4 * j4 + 0]), c4.x);
+            d[4 * j4 + 1] = fmaf(-2.f, __uint_as_float(r[4 * j4 + 1]), c4.y);
+            d[4 * j4 + 2] = fmaf(-2.f, __uint_as_float(r[4 * j4 + 2]), c4.z);
+            d[4 * j4 + 3] = fmaf(-2.f, __uint_as_float(r[4 * j4 + 3]), c4.w);
+          }
+          if (n_valid < 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) d[j] = j < n_valid ? d[j] : INFINITY;
+          }
+          // chunk minimum with NaN propagation (min.NaN): the 32-element scan below runs only for the chunks that
+          // improve the row's best (about two per tile) - the per-element running argmin cost 28 instructions per
+          // element and made this warp role the slowest of the kernel (ncu source view, 3600 instructions per tile)
+          float m8[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) m8[q] = fmin_nan(fmin_nan(d[4 * q], d[4 * q + 1]), fmin_nan(d[4 * q + 2], d[4 * q + 3]));
+          const float m = fmin_nan(fmin_nan(fmin_nan(m8[0], m8[1]), fmin_nan(m8[2], m8[3])), fmin_nan(fmin_nan(m8[4], m8[5]), fmin_nan(m8[6], m8[7])));
+          if (m == m) {                               // no NaN in the chunk: new best iff strictly smaller (ties keep the lower k)
+            if (best_k < 0 || m < best) {
+              int idx = 31;
+#pragma unroll
+              for (int j = 30; j >= 0; --j) idx = d[j] == m ? j : idx;      // first column holding the minimum
+              best = m; best_k = kbase + idx;
+            }
+          } else if (best_k < 0 || best == best) {    // a NaN distance beats any number (torch.min): exact ascending scan
+#pragma unroll 1
+            for (int j = 0; j < n_valid; ++j) {
+              float dj = d[0];
+#pragma unroll
+              for (int t = 1; t < 32; ++t) dj = t == j ? d[t] : dj;
+              if (best_k < 0 || es_better(dj, best)) { best = dj; best_k = kbase + j; }
             }
           }
         }

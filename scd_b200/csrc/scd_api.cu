@@ -245,19 +245,25 @@ int scd_estep(const float* X, int64_t N, int D, const float* C, int K, int64_t* 
   if (int e = make_map_planes(&mc, chi, (uint64_t)K, (uint64_t)D, plane, (uint32_t)p.n_tile, scd::kEsBK)) return e;
   // shared-memory plan: the centroid ring takes what n_tile needs, the rest goes to fp32 X stages in flight
   p.b_plane = p.n_tile * scd::kEsBK * 2;          // n_tile % 16 == 0 -> a multiple of 1024 (swizzle-atom aligned)
+  // converted-operand ring: six stages in the TMEM columns the two accumulators leave free (32 columns per stage, three
+  // above each accumulator) when they exist, else three stages in shared memory
+  const bool tmem_a = p.n_ntiles == 1 && p.n_tile + 3 * 32 <= 256 && p.num_kb >= 3;
+  p.a_stages = tmem_a ? 6 : scd::kEsAStages;
   {
-    const int fixed = scd::EsLayout(0, p.b_plane).total + 1024;
+    const int fixed = scd::EsLayout(0, p.b_plane, tmem_a).total + 1024;
     p.x_stages = std::max(2, std::min(scd::kEsMaxXStages, (scd::kEsSmemLimit - fixed) / scd::kEsXBytes));
   }
-  const int smem = scd::EsLayout(p.x_stages, p.b_plane).total + 1024;
+  const int smem = scd::EsLayout(p.x_stages, p.b_plane, tmem_a).total + 1024;
   if (smem > scd::kEsSmemLimit) return fail("scd_estep: shared-memory plan does not fit (%d bytes)", smem);
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    SCD_CUDA(cudaFuncSetAttribute(scd::estep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
+  static int attr_smem[2] = {0, 0};
+  if (smem > attr_smem[tmem_a]) {
+    if (tmem_a) SCD_CUDA(cudaFuncSetAttribute(scd::estep_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else SCD_CUDA(cudaFuncSetAttribute(scd::estep_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem[tmem_a] = smem;
   }
   const int grid = std::min(device_sm_count(), p.n_row_tiles);
-  scd::estep_tc_kernel<<<grid, scd::kEsThreads, smem, st>>>(mx, mc, p);
+  if (tmem_a) scd::estep_tc_kernel<true><<<grid, scd::kEsThreads, smem, st>>>(mx, mc, p);
+  else scd::estep_tc_kernel<false><<<grid, scd::kEsThreads, smem, st>>>(mx, mc, p);
   SCD_LAUNCH_CHECK("estep_tc_kernel");
   return 0;
 }

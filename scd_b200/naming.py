@@ -144,7 +144,60 @@ def score_topk(feats, zeroshot_weights, k: int = 5, softmax: bool = False, scale
     (``main_unsup.py:519-529`` with ``softmax=True``; ``main_ptsup.py:538-543`` with ``softmax=False``).
     Returns ``(values [n,k] fp32, indices [n,k] int64)``, largest first, ties -> lower index."""
     vocab = _as_vocab(zeroshot_weights)
+    if not torch.is_tensor(feats):
+        feats = torch.from_numpy(np.ascontiguousarray(feats))
+    if not feats.is_cuda and feats.dim() == 2 and int(feats.shape[0]) >= 2 * STREAM_ROWS and feats.dtype == torch.float32:
+        return _score_topk_streamed(feats, vocab, k, softmax, scale)
     vals, idx, _, _ = name_topk_raw(_feats_bf16(feats), vocab, k, softmax, scale)
+    return vals, idx
+
+
+STREAM_ROWS = 74 * 256         # one full wave of 256-row blocks over the 74 CTA pairs of a B200
+
+
+def _score_topk_streamed(feats_host: torch.Tensor, vocab: Vocabulary, k: int, softmax: bool, scale: float):
+    """HOST features (the reference's ``clip_all_feats`` is a NumPy array uploaded per 1024-row batch,
+    ``main_unsup.py:522``): upload in wave-sized row chunks on a copy stream while the previous chunk is cast and
+    scored on the caller's stream, so the PCIe transfer (the bound: 390 MB against 2.8 ms of tensor-core work at C2)
+    hides the kernel instead of preceding it.  Rows are independent, so the per-chunk results are the final rows."""
+    _require_cuda()
+    lib = _lib.load()
+    n, d = int(feats_host.shape[0]), int(feats_host.shape[1])
+    if d != vocab.D:
+        raise ValueError(f'feature width {d} != vocabulary width {vocab.D}')
+    feats_host = feats_host.contiguous()
+    dev = vocab.Wt.device
+    vals = torch.empty(n, k, dtype=torch.float32, device=dev)
+    idx = torch.empty(n, k, dtype=torch.int64, device=dev)
+    main = torch.cuda.current_stream()
+    copy = torch.cuda.Stream()
+    stage = [torch.empty(STREAM_ROWS, d, dtype=torch.float32, device=dev) for _ in range(2)]
+    half = [torch.empty(STREAM_ROWS, d, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    uploaded = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    plans = {}
+    copy.wait_stream(main)
+    for c, lo in enumerate(range(0, n, STREAM_ROWS)):
+        rows = min(STREAM_ROWS, n - lo)
+        b = c & 1
+        with torch.cuda.stream(copy):
+            if c >= 2:
+                copy.wait_event(consumed[b])                       # the cast of chunk c-2 has read this staging buffer
+            stage[b][:rows].copy_(feats_host[lo:lo + rows], non_blocking=True)
+            uploaded[b].record(copy)
+        main.wait_event(uploaded[b])
+        _lib.check(lib.scd_cast_bf16(stage[b].data_ptr(), rows * d, half[b].data_ptr(), main.cuda_stream), 'scd_cast_bf16')
+        consumed[b].record(main)
+        if rows not in plans:
+            plans[rows] = torch.empty(lib.scd_name_topk_workspace_bytes(rows, vocab.V, k), dtype=torch.uint8, device=dev)
+        ws = plans[rows]
+        # half[b] is reused by chunk c+2 only after this launch: same stream, program order
+        _lib.check(lib.scd_name_topk(half[b].data_ptr(), rows, d, vocab.Wt.data_ptr(), vocab.V, float(scale), int(k),
+                                     int(bool(softmax)), vocab.col_offset, vals[lo:lo + rows].data_ptr(),
+                                     idx[lo:lo + rows].data_ptr(), None, None, ws.data_ptr(), ws.numel(), main.cuda_stream),
+                   'scd_name_topk')
+    for t in stage:
+        t.record_stream(copy)
     return vals, idx
 
 

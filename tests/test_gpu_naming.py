@@ -182,3 +182,18 @@ def test_full_size_c2_properties():
     c = 3
     co = naming_oracle.vote(idx.cpu(), y.numpy(), [c], 5)[c]
     assert _counter_list(co) == [(int(a), int(b)) for a, b in zip(names[c].cpu(), counts[c].cpu()) if a >= 0]
+
+
+@pytest.mark.parametrize('softmax', [False, True])
+def test_host_features_stream_in_chunks_and_equal_the_resident_launch(softmax):
+    """score_topk on HOST features uploads wave-sized chunks under the kernel; rows are independent, so the result
+    must equal the single resident launch bit for bit (incl. the ragged last chunk)."""
+    n, d, v = 2 * naming.STREAM_ROWS + 1111, 256, 3000
+    g = torch.Generator().manual_seed(77)
+    feats = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1)
+    W = torch.nn.functional.normalize(torch.randn(v, d, generator=g), dim=1).t().contiguous()
+    vocab = naming.Vocabulary(W)
+    v_res, i_res = naming.score_topk(feats.cuda(), vocab, k=5, softmax=softmax)
+    for host in (feats, feats.pin_memory(), feats.numpy()):
+        v_str, i_str = naming.score_topk(host, vocab, k=5, softmax=softmax)
+        assert torch.equal(i_str, i_res) and torch.equal(v_str, v_res)

@@ -179,7 +179,7 @@ def step_estep_prof():
     """Cycle counters of the E-step kernel's warp roles (scd_debug_set_name_profile)."""
     import torch
     from scd_b200 import kmeans, _lib
-    for (n, d, k) in [(127000, 768, 100), (127000, 768, 1000)]:
+    for (n, d, k) in [(127000, 768, 100), (127000, 768, 200), (127000, 768, 1000)]:
         X = torch.randn(n, d, device='cuda'); X = X / X.norm(dim=1, keepdim=True)
         C = X[:k].clone()
         labels = torch.empty(n, dtype=torch.int64, device='cuda'); acc = torch.zeros(1, dtype=torch.float64, device='cuda')
@@ -200,7 +200,7 @@ def step_estep_prof():
         p = prof.cpu().double()
         names = {0: 'X producer total', 1: 'X producer wait x_empty', 2: 'C producer wait b_empty', 3: 'issuer total', 4: 'issuer wait t_empty',
                  5: 'issuer wait a_full', 6: 'issuer wait b_full', 7: 'converter total', 8: 'converter wait x_full', 9: 'converter wait a_empty',
-                 10: 'epilogue wait t_full', 11: 'tiles'}
+                 10: 'epilogue wait t_full', 11: 'tiles', 12: 'issuer 0 wait token'}
         for kk, nm in names.items():
             col = p[:, kk]
             print(f'   {nm:28s} mean={col.mean():12.0f} min={col.min():12.0f} max={col.max():12.0f}')
