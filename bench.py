@@ -401,7 +401,7 @@ def main():
     achieved = flops / (name_ms * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1 and cfg.name == 'C2':      # the ncu capture is of the single-GPU C2 launch
         with open(tpath) as f:
             traffic = json.load(f).get('name_topk_kernel_dram_bytes_per_launch')
     roofline = dict(bound='tensor', kernel='name_topk_kernel<5> (+ topk_merge)', achieved=round(achieved, 1), peak=peaks['tflops'],

@@ -40,10 +40,13 @@ constexpr int kEsBK = 32;               // k per stage
 constexpr int kEsMaxXStages = 12;       // fp32 X ring: as deep as shared memory allows (host picks EsParams::x_stages)
 constexpr int kEsAStages = 3;           // converted hi/lo ring in shared memory (kTmemA = false)
 constexpr int kEsMaxAStages = 8;        // ... in tensor memory (kTmemA = true): 32 columns per stage, up to 4 above each accumulator
-constexpr int kEsBStages = 3;           // centroid hi/lo ring
+constexpr int kEsBStages = 3;           // centroid hi/lo ring, kTmemA = false
+constexpr int kEsMaxBStages = 6;        // ... kTmemA = true (narrow centroid tiles: six stages still leave >= 6 X stages)
+__host__ __device__ constexpr int es_b_stages(bool tmem_a) { return tmem_a ? kEsMaxBStages : kEsBStages; }
 constexpr int kEsXBytes = kEsBM * kEsBK * 4;          // 16384
 constexpr int kEsAPlane = kEsBM * kEsBK * 2;          // 8192 (one of hi / lo)
-constexpr int kEsConvSets = 2;          // converter warp sets (4 warps each), alternating k-blocks
+constexpr int kEsConvSets = 2;          // converter warp sets (4 warps each), alternating k-blocks; a third set (736 threads,
+                                        // 80 registers) measured no faster: the converters then wait for X (HBM)
 constexpr int kEsIssuers = 3;           // MMA issuer warps (1, 16, 17), k-blocks round-robin
 constexpr int kEsFirstExtraIssuer = 4 + 4 * kEsConvSets + 4;       // warps 16, 17
 constexpr int kEsSecondCProducer = kEsFirstExtraIssuer + kEsIssuers - 1;   // warp 18
@@ -58,9 +61,9 @@ struct EsTail {
   static constexpr int x_empty = x_full + 8 * kEsMaxXStages;
   static constexpr int a_full = x_empty + 8 * kEsMaxXStages;                    // [8]
   static constexpr int a_empty = a_full + 8 * kEsMaxAStages;
-  static constexpr int b_full = a_empty + 8 * kEsMaxAStages;                    // [3]
-  static constexpr int b_empty = b_full + 8 * kEsBStages;
-  static constexpr int t_full = b_empty + 8 * kEsBStages;                       // [2]
+  static constexpr int b_full = a_empty + 8 * kEsMaxAStages;                    // [6]
+  static constexpr int b_empty = b_full + 8 * kEsMaxBStages;
+  static constexpr int t_full = b_empty + 8 * kEsMaxBStages;                    // [2]
   static constexpr int t_empty = t_full + 16;
   static constexpr int drain = t_empty + 16;                                    // every issuer's last commit has landed
   static constexpr int tmem_ptr = drain + 16;
@@ -77,7 +80,8 @@ struct EsParams {
   int n_ntiles;            // ceil(K / 256) (1 for K <= 256)
   int num_kb;              // ceil(D / 32)
   int n_row_tiles;
-  int x_stages;            // depth of the fp32 X ring (2 .. kEsMaxXStages)
+  int x_stages;            // depth of the fp32 X ring (2 .. kEsMaxXStages), EVEN: a stage must belong to one producer /
+                           // converter-set pair (see scd_estep)
   int b_plane;             // bytes of one centroid plane stage: n_tile * 64 (n_tile % 16 == 0, so a multiple of 1024)
   int a_stages;            // depth of the converted-operand ring: kEsAStages = 3 (shared memory) or 6 (TMEM) - a multiple of
                            // the issuer count; never more than 2 * num_kb, so the 4-deep ||x||^2 ring cannot be overrun
@@ -95,7 +99,7 @@ struct EsLayout {
     x_off = 0;
     a_off = x_off + x_stages * kEsXBytes;
     b_off = a_off + (tmem_a ? 0 : kEsAStages * 2 * kEsAPlane);
-    tail_off = b_off + kEsBStages * 2 * b_plane;
+    tail_off = b_off + es_b_stages(tmem_a) * 2 * b_plane;
     total = tail_off + EsTail::total;
   }
 };
@@ -151,6 +155,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const EsLayout L(p.x_stages, p.b_plane, kTmemA);
   const int kEsXStages = p.x_stages;
   const int n_as = p.a_stages;
+  constexpr uint32_t kNB = (uint32_t)es_b_stages(kTmemA);      // centroid ring depth
 
   auto bar = [&](int base, int i) { return sbase + L.tail_off + base + 8 * i; };
   const bool prof = p.prof != nullptr;
@@ -169,7 +174,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kEsXStages; ++s) { ptx::mbar_init(bar(EsTail::x_full, s), 1); ptx::mbar_init(bar(EsTail::x_empty, s), 4); }
     for (int s = 0; s < n_as; ++s) { ptx::mbar_init(bar(EsTail::a_full, s), 4); ptx::mbar_init(bar(EsTail::a_empty, s), 1); }
-    for (int s = 0; s < kEsBStages; ++s) { ptx::mbar_init(bar(EsTail::b_full, s), 1); ptx::mbar_init(bar(EsTail::b_empty, s), 1); }
+    for (int s = 0; s < kNB; ++s) { ptx::mbar_init(bar(EsTail::b_full, s), 1); ptx::mbar_init(bar(EsTail::b_empty, s), 1); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(bar(EsTail::t_full, b), 1); ptx::mbar_init(bar(EsTail::t_empty, b), 4); }
     ptx::mbar_init(bar(EsTail::drain, 0), kEsIssuers);
     ptx::fence_mbar_init_cluster();
@@ -224,7 +229,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         for (int nt = 0; nt < p.n_ntiles; ++nt) {
           for (int kb = 0; kb < nkb; ++kb, ++g) {
             if ((g & 1u) != me) continue;
-            const uint32_t bs = g % kEsBStages, bph = (g / kEsBStages) & 1u;
+            const uint32_t bs = g % kNB, bph = (g / kNB) & 1u;
             twait(bar(EsTail::b_empty, bs), bph ^ 1, 710 + bs, w_be);
             ptx::mbar_arrive_expect_tx(bar(EsTail::b_full, bs), b_bytes);
             ptx::tma_load_3d(sbase + L.b_off + bs * 2 * p.b_plane, &map_c, bar(EsTail::b_full, bs), kb * kEsBK, nt * 256, 0,
@@ -244,22 +249,26 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // round-robin: each prepares its six MMAs' operands and does its barrier waits while the other two warps' MMAs run,
     // waits for a named-barrier token (ids 1..3), fires its MMAs back to back and hands the token on before committing.
     // The token keeps the issue order = the pipe's execution order, so the last k-block's commit covers the whole tile.
-    // Issuer `me` owns k-blocks g = me, me + 3, ...: with 3 centroid stages and 3 (or 6) A stages its centroid stage is
-    // always `me` and its A stage is `me` (or alternates me, me + 3), so every descriptor is LOOP INVARIANT and can stay
-    // in uniform registers for the whole kernel (the rate the micro-benchmark reaches with invariant descriptors).
-    static_assert(kEsIssuers == kEsBStages, "an issuer's centroid stage must be constant");
+    // Issuer `me` owns k-blocks g = me, me + 3, ...: the centroid and A rings are 3 or 6 deep, so its stages are always
+    // `me` (or alternate me, me + 3) and every descriptor is LOOP INVARIANT: computed once, selected by the unroll index.
+    static_assert(kEsBStages == kEsIssuers && kEsMaxBStages == 2 * kEsIssuers, "an issuer's centroid stages must be fixed");
+    static_assert(kEsConvSets == 2, "X producers and converter sets pair up by the parity of g (even X ring, see scd_estep)");
     constexpr int kASets = kTmemA ? 2 : 1;                       // A stages per issuer (a_stages = 3 * kASets)
+    constexpr int kBSets = (int)kNB / kEsIssuers;                // centroid stages per issuer
+    constexpr int kSets = kASets > kBSets ? kASets : kBSets;     // k-blocks per unrolled issuer step
     const uint32_t me = warp == 1 ? 0u : warp - kEsFirstExtraIssuer + 1u;
     const uint32_t idesc = ptx::make_idesc_bf16_f32(kEsBM, (uint32_t)p.n_tile);
-    const uint32_t bs = me;
-    const uint32_t b_hi = sbase + L.b_off + bs * 2 * p.b_plane, b_lo = b_hi + p.b_plane;
-    uint64_t dbh[2], dbl[2], dah[kASets][2], dal[kASets][2];
+    uint64_t dbh[kBSets][2], dbl[kBSets][2], dah[kASets][2], dal[kASets][2];
     uint32_t ath[kASets][2], atl[kASets][2];
 #pragma unroll
     for (int kk = 0; kk < kEsBK / 16; ++kk) {
       const uint32_t ko = kk * 32;                               // 16 bf16 = 32 bytes inside the 64-byte swizzle atom
-      dbh[kk] = ptx::make_kmajor_desc(b_hi + ko, 64);
-      dbl[kk] = ptx::make_kmajor_desc(b_lo + ko, 64);
+#pragma unroll
+      for (int u = 0; u < kBSets; ++u) {
+        const uint32_t b_hi = sbase + L.b_off + (me + 3u * u) * 2 * p.b_plane;
+        dbh[u][kk] = ptx::make_kmajor_desc(b_hi + ko, 64);
+        dbl[u][kk] = ptx::make_kmajor_desc(b_hi + p.b_plane + ko, 64);
+      }
 #pragma unroll
       for (int u = 0; u < kASets; ++u) {
         const int as = (int)me + 3 * u;
@@ -280,13 +289,14 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const bool iprof = prof && me == 0;
     long long w_te = 0, w_af = 0, w_bf = 0, w_tok = 0; const long long t0 = iprof ? clock64() : 0;
     uint32_t kb = me % (uint32_t)nkb, tile_no = me / (uint32_t)nkb;      // of k-block g, advanced by 3 per step
-    for (uint32_t g0 = me; g0 < g_total; g0 += kEsIssuers * kASets) {
+    for (uint32_t g0 = me; g0 < g_total; g0 += kEsIssuers * kSets) {
 #pragma unroll
-      for (int u = 0; u < kASets; ++u) {
+      for (int u = 0; u < kSets; ++u) {
         const uint32_t g = g0 + kEsIssuers * u;
         if (g >= g_total) break;
-        const uint32_t as = me + 3u * (uint32_t)u;
-        const uint32_t aph = (g / (uint32_t)(kEsIssuers * kASets)) & 1u, bph = (g / kEsBStages) & 1u;
+        const int ua = u % kASets, ub = u % kBSets;                  // compile-time after unrolling
+        const uint32_t as = me + 3u * (uint32_t)ua, bs = me + 3u * (uint32_t)ub;
+        const uint32_t aph = (g / (uint32_t)(kEsIssuers * kASets)) & 1u, bph = (g / kNB) & 1u;
         const uint32_t buf = tile_no & 1u;
         const uint32_t d_tmem = tmem_base + buf * 256;
         if (kb == 0) {
@@ -306,13 +316,13 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
           for (int kk = 0; kk < kEsBK / 16; ++kk) {
             if constexpr (kTmemA) {
-              ptx::umma_bf16_ts<1>(d_tmem, ath[u][kk], dbh[kk], idesc, (kb | (uint32_t)kk) != 0 ? 1u : 0u);
-              ptx::umma_bf16_ts<1>(d_tmem, ath[u][kk], dbl[kk], idesc, 1u);
-              ptx::umma_bf16_ts<1>(d_tmem, atl[u][kk], dbh[kk], idesc, 1u);
+              ptx::umma_bf16_ts<1>(d_tmem, ath[ua][kk], dbh[ub][kk], idesc, (kb | (uint32_t)kk) != 0 ? 1u : 0u);
+              ptx::umma_bf16_ts<1>(d_tmem, ath[ua][kk], dbl[ub][kk], idesc, 1u);
+              ptx::umma_bf16_ts<1>(d_tmem, atl[ua][kk], dbh[ub][kk], idesc, 1u);
             } else {
-              ptx::umma_bf16<1>(d_tmem, dah[u][kk], dbh[kk], idesc, (kb | (uint32_t)kk) != 0 ? 1u : 0u);
-              ptx::umma_bf16<1>(d_tmem, dah[u][kk], dbl[kk], idesc, 1u);
-              ptx::umma_bf16<1>(d_tmem, dal[u][kk], dbh[kk], idesc, 1u);
+              ptx::umma_bf16<1>(d_tmem, dah[ua][kk], dbh[ub][kk], idesc, (kb | (uint32_t)kk) != 0 ? 1u : 0u);
+              ptx::umma_bf16<1>(d_tmem, dah[ua][kk], dbl[ub][kk], idesc, 1u);
+              ptx::umma_bf16<1>(d_tmem, dal[ua][kk], dbh[ub][kk], idesc, 1u);
             }
           }
         }
@@ -416,8 +426,8 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar(EsTail::a_full, as));
           }
-          xs += kEsConvSets; if (xs >= (uint32_t)kEsXStages) { xs -= (uint32_t)kEsXStages; xph ^= 1u; }
-          as += kEsConvSets; if (as >= (uint32_t)n_as) { as -= (uint32_t)n_as; aph ^= 1u; }
+          xs += kEsConvSets; while (xs >= (uint32_t)kEsXStages) { xs -= (uint32_t)kEsXStages; xph ^= 1u; }
+          as += kEsConvSets; while (as >= (uint32_t)n_as) { as -= (uint32_t)n_as; aph ^= 1u; }
         }
       }
     }
@@ -452,10 +462,20 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll 1
         for (int c = 0; c * 32 < n_here; ++c) {
           uint32_t r[32];
-          ptx::tmem_ld_32x32(taddr + c * 32, r);     // columns past n_here are zero-padded centroids or stale TMEM, masked below
+          // Never read accumulator columns the MMA did not write (n_tile is a multiple of 16, so a ragged last chunk
+          // is exactly 16 columns): reading never-written tensor memory made about one launch in 10^4 die with an
+          // "unspecified launch failure" - only for tile widths with n_tile % 32 == 16 whose upper columns nothing
+          // ever writes (K = 161 / 200; randomised stress tools/estep_stress2.py, profiles/r1q_estep_stress.txt).
+          if (c * 32 + 32 <= p.n_tile) {
+            ptx::tmem_ld_32x32(taddr + c * 32, r);
+          } else {
+#pragma unroll
+            for (int j = 16; j < 32; ++j) r[j] = 0u;
+            ptx::tmem_ld_32x16(taddr + c * 32, r);
+          }
           ptx::tmem_ld_wait(r);
           const int kbase = k0 + c * 32;
-          const int n_valid = min(n_here - c * 32, 32);
+          const int n_valid = min(n_here - c * 32, 32);    // <= 16 in the ragged chunk: columns past it are masked below
           float d[32];
           const float4* cn4 = reinterpret_cast<const float4*>(cn + kbase);
 #pragma unroll

@@ -465,8 +465,9 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         ptx::tc_fence_after_sync();
         const long long tr0 = trace ? clock64() : 0;
         const uint32_t taddr = tmem_base + lane_addr + buf * kAccStride + half * kHalfCols;
-        // four 32-column chunks per half; the second half has only 96 columns (its fourth load reads the TMEM-resident
-        // A operand and is ignored: n_valid - 96 <= 0)
+        // four 32-column chunks in the first half, three in the second (96 columns).  Its fourth chunk would be the
+        // TMEM-resident A columns: never read tensor memory that may not have been written (for D <= 64 the second
+        // A k-block does not exist) - see the E-step epilogue for what that costs
         uint32_t ra[32], rb[32];
         ptx::tmem_ld_32x32(taddr, ra);
         ptx::tmem_ld_wait(ra);                                   // ra = chunk 0
@@ -476,15 +477,15 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         ptx::tmem_ld_32x32(taddr + 64, ra);
         process(rb, col0 + 32, n_valid - 32);
         ptx::tmem_ld_wait(ra);                                   // ra = chunk 2
-        ptx::tmem_ld_32x32(taddr + 96, rb);
+        if (half == 0) ptx::tmem_ld_32x32(taddr + 96, rb);
         process(ra, col0 + 64, n_valid - 64);
-        ptx::tmem_ld_wait(rb);                                   // rb = chunk 3
+        if (half == 0) ptx::tmem_ld_wait(rb);                    // rb = chunk 3
         // this warp's share of the accumulator buffer is in registers: hand it back to the MMA issuer
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_remote(tmem_empty_bar(buf) & ptx::kPeerBitMask);
         const long long tr1 = trace ? clock64() : 0;
-        process(rb, col0 + 96, n_valid - 96);
+        if (half == 0) process(rb, col0 + 96, n_valid - 96);
         if (trace && lane == 0 && n_ev < 128) { trace[3 * n_ev] = tr0; trace[3 * n_ev + 1] = tr1; trace[3 * n_ev + 2] = clock64(); ++n_ev; }
       }
 

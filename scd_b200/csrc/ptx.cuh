@@ -129,26 +129,50 @@ __device__ __forceinline__ bool mbar_try_wait2(uint32_t bar0, uint32_t bar1, uin
 }
 // Bounded wait: a protocol bug must end in a trap (launch failure the host reports), never in a
 // hung GPU.  The bound is wall-clock (globaltimer), 4 s.
+// The 64-bit %globaltimer is NOT read atomically (SASS: a CS2R pair on the LO / HI halves; LO wraps every 4.29 s): a read
+// that straddles the wrap is off by +-2^32 ns, which a single `now - t0 > 4 s` test takes for a timeout.  Randomised
+// stress (tools/estep_stress2.py) hit that about once per 10^4 launches as an "unspecified launch failure" with no
+// delay - in every kernel that waits on an mbarrier.  So: signed differences, a torn or backward reading re-arms the
+// clock, and the bound must hold on three consecutive probes (a torn reading does not repeat) before the trap.
 __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity, int tag) {
   printf("[scd_b200] mbarrier wait timed out: block %d thread %d tag %d bar 0x%x parity %u\n",
          (int)blockIdx.x, (int)threadIdx.x, tag, bar, parity);
   __trap();
 }
+// two consecutive readings that agree to within a second: neither is torn
+__device__ __forceinline__ uint64_t globaltimer_stable_ns() {
+  uint64_t a = globaltimer_ns(), b = globaltimer_ns();
+  while ((long long)(b - a) < 0 || b - a > 1000000000ull) { a = b; b = globaltimer_ns(); }
+  return b;
+}
+struct WaitClock {
+  uint64_t t0;
+  uint32_t spins;
+  int over;
+  __device__ __forceinline__ WaitClock() : t0(globaltimer_stable_ns()), spins(0), over(0) {}
+  // called once per failed probe; true when the wait has really lasted longer than the bound
+  __device__ __forceinline__ bool expired() {
+    if ((++spins & 0x3FFu) != 0) return false;
+    const long long dt = (long long)(globaltimer_ns() - t0);
+    if (dt < 0) { over = 0; return false; }                                   // torn / backward reading: ignore it
+    if (dt > 4000000000ll && dt < 3600000000000ll) return ++over >= 3;
+    over = 0;
+    return false;
+  }
+};
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
-  uint32_t spins = 0;
+  WaitClock clk;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0 && globaltimer_ns() - t0 > 4000000000ull) mbar_timeout_trap(bar, parity, tag);
+    if (clk.expired()) mbar_timeout_trap(bar, parity, tag);
   }
 }
 
 __device__ __forceinline__ void mbar_wait2(uint32_t bar0, uint32_t bar1, uint32_t parity, int tag = 0) {
   if (mbar_try_wait2(bar0, bar1, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
-  uint32_t spins = 0;
+  WaitClock clk;
   while (!mbar_try_wait2(bar0, bar1, parity)) {
-    if ((++spins & 0x3FFu) == 0 && globaltimer_ns() - t0 > 4000000000ull) mbar_timeout_trap(bar0, parity, tag);
+    if (clk.expired()) mbar_timeout_trap(bar0, parity, tag);
   }
 }
 
@@ -292,6 +316,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns -> the first 16 registers (the others are left as they are)
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }

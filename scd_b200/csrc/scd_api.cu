@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -252,6 +253,13 @@ int scd_estep(const float* X, int64_t N, int D, const float* C, int K, int64_t* 
   {
     const int fixed = scd::EsLayout(0, p.b_plane, tmem_a).total + 1024;
     p.x_stages = std::max(2, std::min(scd::kEsMaxXStages, (scd::kEsSmemLimit - fixed) / scd::kEsXBytes));
+    // EVEN, always: k-block g is loaded by X producer (g & 1) and read by converter set (g & 1).  With an even ring a
+    // stage belongs to one producer / set pair and its x_full phases are consumed in order.  With an odd ring the two
+    // sets alternate on every stage, and a set that runs one ring revolution ahead of the other sees the parity of
+    // the phase before last as "its" phase (parity aliasing): it reads a stale tile, releases the stage early, and the
+    // producers then double-arrive on x_full - about one launch in 10^3..10^4 died with "unspecified launch failure"
+    // for K = 200 / 208 / 224 (five stages) until this was found with tools/estep_stress2.py.
+    p.x_stages &= ~1;
   }
   const int smem = scd::EsLayout(p.x_stages, p.b_plane, tmem_a).total + 1024;
   if (smem > scd::kEsSmemLimit) return fail("scd_estep: shared-memory plan does not fit (%d bytes)", smem);
