@@ -355,10 +355,16 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               at[kk] = tmem_base + a_tmem_col(a_in_tmem ? kb : 0, kk);
               asm volatile("" : "+l"(bd[kk]), "+l"(ad[kk]), "+r"(at[kk]));
             }
-            if (kb == 0) { const long long c0 = prof ? clock64() : 0;
+            // Accumulator buffer free?  Waited for ahead of the token - except when a tile is a single k-block (D <= 64):
+            // an issuer then sits three tiles ahead of the one it issued last, the release it needs (tile - 2) can
+            // still have the previous release (tile - 4) pending, and a parity wait cannot tell those two phases apart
+            // (it returned at once, the MMAs overwrote a buffer the epilogue was reading, and the pair deadlocked).
+            // After the token every earlier tile has been issued, so tile - 4 has certainly been released.
+            const bool te_after_token = nkb == 1;
+            if (kb == 0 && !te_after_token) { const long long c0 = prof ? clock64() : 0;
               ptx::mbar_wait(tmem_empty_bar(buf), ((tile_no >> 1) & 1u) ^ 1u, 300 + buf);
               if (prof) pf_te += clock64() - c0; }
-            if (t == 0) { const long long c0 = prof ? clock64() : 0;
+            if (t == 0 && !te_after_token) { const long long c0 = prof ? clock64() : 0;
               ptx::mbar_wait(a_full_bar(kb), my_item_no & 1, 400 + kb);
               if (prof) pf_a += clock64() - c0; }
             { const long long c0 = prof ? clock64() : 0;
@@ -370,6 +376,11 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             if (g > 0) { const long long c0 = prof ? clock64() : 0;
               ptx::named_bar_sync(1 + me, 64);
               if (prof) pf_tok += clock64() - c0; }
+            if (te_after_token) {          // same reasoning for the rows of the item: with one k-block per tile the
+              if (kb == 0) ptx::mbar_wait(tmem_empty_bar(buf), ((tile_no >> 1) & 1u) ^ 1u, 310 + buf);    // issuers
+              if (t == 0) ptx::mbar_wait(a_full_bar(kb), my_item_no & 1, 410 + kb);    // take turns on a_full(0) too
+              ptx::tc_fence_after_sync();
+            }
             const long long tr1 = trace ? clock64() : 0;
             const bool elected = ptx::elect_one();
             if (elected) {

@@ -197,3 +197,19 @@ def test_host_features_stream_in_chunks_and_equal_the_resident_launch(softmax):
     for host in (feats, feats.pin_memory(), feats.numpy()):
         v_str, i_str = naming.score_topk(host, vocab, k=5, softmax=softmax)
         assert torch.equal(i_str, i_res) and torch.equal(v_str, v_res)
+
+
+@pytest.mark.parametrize('n,v,d,k', [(40000, 11000, 64, 5), (40000, 300, 64, 1), (60000, 500, 40, 5), (40000, 5000, 512, 5),
+                                     (127000, 100, 768, 1)])
+def test_several_row_blocks_per_cta_pair_at_narrow_widths(n, v, d, k):
+    """Regression: with one k-block per tile (D <= 64) and more than one work item per CTA pair the MMA issuers ran
+    three tiles ahead of their parity waits and the pair deadlocked (found by tools/naming_stress.py).  Checked on a
+    row sample against torch, margins as everywhere else."""
+    g = torch.Generator().manual_seed(n + v + d)
+    X = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1).bfloat16()
+    W = torch.nn.functional.normalize(torch.randn(v, d, generator=g), dim=1).bfloat16()
+    vocab = naming.Vocabulary.from_rows(W.cuda())
+    for _ in range(3):                                    # back to back, no sync in between
+        vals, idx, _, _ = naming.name_topk_raw(X.cuda(), vocab, k, False)
+    rows = torch.randperm(n, generator=g)[:1500]
+    _check_topk(vals[rows.cuda()], idx[rows.cuda()], X[rows].float(), W.float().t().contiguous(), k, 'ptsup', LOGIT_ATOL)

@@ -1,0 +1,57 @@
+"""One-process randomized stress of the fused scoring/top-k kernel: shapes interleaved, no sync inside a batch; every
+launch must reproduce the first launch of its shape bit for bit (values and indices), and the first launch is checked
+against torch on a row sample."""
+import random
+import sys
+import time
+
+import torch
+sys.path.insert(0, '.')
+from scd_b200 import naming
+
+random.seed(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+budget_s = float(sys.argv[2]) if len(sys.argv) > 2 else 40.0
+shapes = [(127000, 21000, 768, 5, False), (20000, 21000, 768, 5, True), (5000, 3000, 768, 5, False), (40000, 11000, 64, 5, False),
+          (19000, 5000, 128, 1, False), (3000, 100, 768, 1, False), (70000, 2000, 512, 8, True), (513, 257, 72, 2, False),
+          (30000, 82000, 768, 5, False)]
+data = {}
+for (n, v, d, k, sm) in shapes:
+    g = torch.Generator(device='cuda').manual_seed(n + v)
+    X = torch.randn(n, d, device='cuda', generator=g); X = (X / X.norm(dim=1, keepdim=True)).bfloat16()
+    W = torch.randn(v, d, device='cuda', generator=g); W = (W / W.norm(dim=1, keepdim=True)).bfloat16()
+    vocab = naming.Vocabulary.from_rows(W)
+    plan = naming.TopKPlan(n, v, k, 'cuda')
+    vals, idx, _, _ = plan.run(X, vocab, sm)
+    try:
+        torch.cuda.synchronize()
+    except Exception as e:
+        print('SETUP LAUNCH FAILED for shape', (n, v, d, k, sm), ':', str(e).splitlines()[0], flush=True)
+        sys.exit(3)
+    rows = torch.randperm(n, device='cuda')[:1024]
+    logits = 100. * (X[rows].float() @ W.float().t())
+    if sm:
+        logits = torch.softmax(logits, dim=1)
+    rv, ri = logits.topk(min(k, v), 1, True, True)
+    agree = float((idx[rows][:, :ri.shape[1]] == ri).float().mean())
+    assert agree > 0.995, (n, v, d, k, sm, agree)
+    data[(n, v, d, k, sm)] = (X, vocab, plan, vals.clone(), idx.clone())
+torch.cuda.synchronize()
+t0, launches, batches = time.time(), 0, 0
+while time.time() - t0 < budget_s:
+    seq = [random.choice(shapes) for _ in range(random.randint(1, 8))]
+    for sh in seq:
+        X, vocab, plan, v0, i0 = data[sh]
+        plan.run(X, vocab, sh[4])
+        launches += 1
+    try:
+        torch.cuda.synchronize()
+    except Exception as e:
+        print('FAILED after', launches, 'launches; last batch', seq, ':', str(e).splitlines()[0], flush=True)
+        sys.exit(1)
+    for sh in set(seq):
+        X, vocab, plan, v0, i0 = data[sh]
+        if not (torch.equal(plan.idx, i0) and torch.equal(plan.vals, v0)):
+            print('NOT REPRODUCIBLE', sh, int((plan.idx != i0).sum()), flush=True)
+            sys.exit(2)
+    batches += 1
+print(f'ok: {launches} launches in {batches} batches, all bit-identical to the first launch of their shape')
