@@ -28,6 +28,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# stdout carries exactly one JSON line: NCCL_DEBUG=VERSION (set in some images) makes NCCL print its banner there
+if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+    os.environ['NCCL_DEBUG'] = 'WARN'
+
 import numpy as np
 import torch
 
