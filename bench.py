@@ -28,10 +28,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# stdout carries exactly one JSON line: NCCL_DEBUG=VERSION (set in some images) makes NCCL print its banner there
-if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-    os.environ['NCCL_DEBUG'] = 'WARN'
-
 import numpy as np
 import torch
 
@@ -343,6 +339,11 @@ def main():
 
     # -------------------------------------------------------------------------------- B200 arm
     assert torch.cuda.is_available(), 'bench.py needs a GPU (the B200 path has no CPU fallback)'
+    # stdout carries exactly ONE JSON line: NCCL prints its version banner on fd 1 when NCCL_DEBUG is set (seen on the
+    # 2-GPU box), so everything libraries write to fd 1 is sent to stderr and the line goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     group = None
     if world > 1:
@@ -442,7 +443,8 @@ def main():
                     launch_mode='cuda-graph replay' if graphed else 'eager',
                     roofline=roofline, cpu_baseline=cpu_baseline,
                     split=dict(naming_ms=round(name_ms, 4), rest_ms=round(ms_per_step - name_ms, 4)))
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + '\n')
+        real_stdout.flush()
     if world > 1:
         # Leave without tearing NCCL down: destroy_process_group() / interpreter exit can block for minutes while
         # a CUDA graph that captured NCCL kernels is still alive (seen on the 2-GPU box).  Every rank has passed
