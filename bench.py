@@ -32,7 +32,7 @@ import numpy as np
 import torch
 
 METRIC = 'ms per naming round (k-means iter + vocab top-k + vote)'
-CPU_SAMPLE_ROWS = 8192
+CPU_SAMPLE_ROWS = int(os.environ.get('SCD_BENCH_CPU_ROWS', '8192'))      # rows of the bounded CPU sample (tests shrink it)
 
 
 # ------------------------------------------------------------------------------------------ helpers
