@@ -32,7 +32,8 @@ def _assert_labels(labels_gpu, X, C):
     assert torch.equal(labels_gpu.cpu()[ok], want[ok])
 
 
-@pytest.mark.parametrize('n,d,k', [(600, 64, 12), (1, 8, 1), (130, 20, 65), (1000, 768, 100), (257, 4, 3), (4096, 768, 200)])
+@pytest.mark.parametrize('n,d,k', [(600, 64, 12), (1, 8, 1), (130, 20, 65), (1000, 768, 100), (257, 4, 3), (4096, 768, 200),
+                                   (5000, 128, 12), (3000, 768, 17), (300, 768, 3), (5000, 96, 33), (129, 104, 1)])
 def test_pairwise_distance_and_estep(n, d, k):
     g = torch.Generator().manual_seed(n + d + k)
     X = synth.unit_rows(torch.randn(n, d, generator=g))
