@@ -67,10 +67,10 @@ def contingency(y_pred, y_true, dim: int | None = None, mask=None):
     return w.cpu().numpy(), first.cpu().numpy(), colm.cpu().numpy()
 
 
-def split_cluster_acc_v2(y_true, y_pred, mask, return_ind_map=False):
-    """Clustering accuracy after one Hungarian matching on all rows; 'old' = classes met under ``mask``, 'new' =
-    classes met under ``~mask`` (``cluster_and_log_utils.py:28-76``).  Returns ``(total_acc, old_acc, new_acc[, ind_map])``."""
-    w, _, col_old = contingency(y_pred, y_true, mask=mask)
+def _cluster_acc_from_contingency(w, col_old, return_ind_map=False):
+    """Host half of ``split_cluster_acc_v2`` (``cluster_and_log_utils.py:52-76``) on the ``D x D`` contingency matrix and
+    the per-class counts of rows under the old/new mask: Hungarian matching with the reference's tie-breaking, then
+    the reference's integer sums and float64 divisions."""
     n = int(w.sum())
     col_all = w.sum(axis=0)
     old_classes = np.nonzero(col_old)[0]                                   # set(y_true[mask]), :43
@@ -91,11 +91,16 @@ def split_cluster_acc_v2(y_true, y_pred, mask, return_ind_map=False):
     return total_acc, accs[0], accs[1]
 
 
-def evaluate_semantic_acc(u_targets, cidx_to_cname, u_preds, cand_names):
-    """``main_unsup.py:149-167``: ``(semantic_acc_avg, semantic_acc_all)`` - a row matches when the name of its class
-    equals the name voted for its cluster.  The per-row string compares of the reference become one contingency
-    matrix; names are compared once per (cluster, class) cell."""
-    w, first, _ = contingency(u_preds, u_targets)
+def split_cluster_acc_v2(y_true, y_pred, mask, return_ind_map=False):
+    """Clustering accuracy after one Hungarian matching on all rows; 'old' = classes met under ``mask``, 'new' =
+    classes met under ``~mask`` (``cluster_and_log_utils.py:28-76``).  Returns ``(total_acc, old_acc, new_acc[, ind_map])``."""
+    w, _, col_old = contingency(y_pred, y_true, mask=mask)
+    return _cluster_acc_from_contingency(w, col_old, return_ind_map)
+
+
+def _semantic_acc_from_contingency(w, first, cidx_to_cname, cand_names):
+    """Host half of ``evaluate_semantic_acc`` (``main_unsup.py:149-167``): names are compared once per (cluster, class)
+    cell; the per-name accuracies are summed in the order the class names are first met in the rows (``first``)."""
     n = int(w.sum())
     col_all = w.sum(axis=0)
     classes = [int(c) for c in np.argsort(first, kind='stable') if col_all[c] > 0]      # order of first appearance (:152)
@@ -113,6 +118,14 @@ def evaluate_semantic_acc(u_targets, cidx_to_cname, u_preds, cand_names):
         matched_all += hit
     acc = {name: hit / float(cnt) for name, (hit, cnt) in per_name.items()}             # :160-163
     return float(sum(acc.values())) / len(acc.values()), matched_all / float(n)         # :165-167
+
+
+def evaluate_semantic_acc(u_targets, cidx_to_cname, u_preds, cand_names):
+    """``main_unsup.py:149-167``: ``(semantic_acc_avg, semantic_acc_all)`` - a row matches when the name of its class
+    equals the name voted for its cluster.  The per-row string compares of the reference become one contingency
+    matrix (``scd_contingency``)."""
+    w, first, _ = contingency(u_preds, u_targets)
+    return _semantic_acc_from_contingency(w, first, cidx_to_cname, cand_names)
 
 
 def _target_name_idx(targets, cidx_to_cname, nouns):
