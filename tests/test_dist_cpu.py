@@ -65,6 +65,7 @@ def _worker(rank, world, port, k, d):
         dist.destroy_process_group()
 
 
-@pytest.mark.timeout(120)
-def test_packed_allreduce_and_row_gather_world2_gloo():
-    mp.spawn(_worker, args=(2, _free_port(), 6, 16), nprocs=2, join=True)
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize('world', [2, 3])           # 3: ragged shards (101 rows -> 34 / 34 / 33), as on 4 or 8 GPUs
+def test_packed_allreduce_and_row_gather_gloo(world):
+    mp.spawn(_worker, args=(world, _free_port(), 6, 16), nprocs=world, join=True)
