@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU visit: E-step bring-up + counters and the k-means parity tests only
+# GPU visit: E-step bring-up + per-role cycle counters and the k-means parity tests
 mkdir -p gpurun_out
 TAG=${1:-v3}
 timeout 300 python tools/gpu_diag.py kmeans estep_prof > gpurun_out/${TAG}_diag.log 2>&1
