@@ -52,13 +52,23 @@ inline cudaStream_t as_stream(scd_stream_t s) { return reinterpret_cast<cudaStre
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Per-device caches: function attributes and SM counts belong to a device, and although the intended deployment is one
+// process per GPU, a host process may switch devices between calls.
+constexpr int kMaxDevices = 64;
+
+int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return dev;
+}
+
 int device_sm_count() {
-  static int cached = 0;
-  if (cached) return cached;
-  int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device_slot();
+  if (cached[dev]) return cached[dev];
+  int n = 0;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-  cached = n;
+  cached[dev] = n;
   return n;
 }
 
@@ -165,11 +175,12 @@ bool plan_naming(int64_t N, int64_t V, int k, NamePlan* pl) {
 
 template <int KT>
 int launch_name_topk(const CUtensorMap& mx, const CUtensorMap& mw, const scd::NameParams& p, int n_pairs, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set[kMaxDevices] = {};
   const int smem = scd::NameSmem::total + 1024;
-  if (!attr_set) {
+  const int dev = current_device_slot();
+  if (!attr_set[dev]) {
     SCD_CUDA(cudaFuncSetAttribute(scd::name_topk_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   scd::name_topk_kernel<KT><<<2 * n_pairs, scd::kNameThreads, smem, st>>>(mx, mw, p);
   SCD_LAUNCH_CHECK("name_topk_kernel");
@@ -263,11 +274,12 @@ int scd_estep(const float* X, int64_t N, int D, const float* C, int K, int64_t* 
   }
   const int smem = scd::EsLayout(p.x_stages, p.b_plane, tmem_a).total + 1024;
   if (smem > scd::kEsSmemLimit) return fail("scd_estep: shared-memory plan does not fit (%d bytes)", smem);
-  static int attr_smem[2] = {0, 0};
-  if (smem > attr_smem[tmem_a]) {
+  static int attr_smem[kMaxDevices][2] = {};
+  const int dev = current_device_slot();
+  if (smem > attr_smem[dev][tmem_a]) {
     if (tmem_a) SCD_CUDA(cudaFuncSetAttribute(scd::estep_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     else SCD_CUDA(cudaFuncSetAttribute(scd::estep_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem[tmem_a] = smem;
+    attr_smem[dev][tmem_a] = smem;
   }
   const int grid = std::min(device_sm_count(), p.n_row_tiles);
   if (tmem_a) scd::estep_tc_kernel<true><<<grid, scd::kEsThreads, smem, st>>>(mx, mc, p);
@@ -532,10 +544,11 @@ static int launch_vote(const int64_t* topk_idx, int k_total, int k_used, const i
                        const int64_t* excluded, int n_excluded, int M, int64_t* out_names, int32_t* out_counts,
                        int32_t* out_distinct, int32_t* overflow, cudaStream_t st) {
   SCD_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), st));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  const int dev = current_device_slot();
+  if (!attr_set[dev]) {
     SCD_CUDA(cudaFuncSetAttribute(scd::vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scd::kVoteSmemBytes));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   scd::vote_kernel<<<K, scd::kVoteThreads, scd::kVoteSmemBytes, st>>>(
       reinterpret_cast<const long long*>(topk_idx), k_total, k_used, order, offsets, K, reinterpret_cast<const long long*>(excluded),
