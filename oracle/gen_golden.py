@@ -428,9 +428,13 @@ def gen_eval(ref):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--ref', default='/root/reference')
+    ap.add_argument('--out', default=None, help='write the fixtures here instead of tests/golden (used by the reproducibility test)')
     ap.add_argument('--only', default=None, choices=[None, 'kmeans', 'constrained', 'hungarian', 'naming', 'eval'],
                     help='regenerate one fixture family (the others are left as committed)')
     a = ap.parse_args()
+    global OUT
+    if a.out:
+        OUT = os.path.abspath(a.out)
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)          # fixtures must not depend on the thread count of this box
     km_local, km_gcd, lang, cu = import_reference(a.ref)
