@@ -114,6 +114,11 @@ SCD_API int scd_gather_rows_bf16(const scd_bf16_t* Wt, const int64_t* sel, int n
  * row_max/row_sumexp (nullable, [N]): unscaled row max and sum exp(scale*(x-max)) for cross-shard softmax.
  * The N x V score matrix is never written. */
 SCD_API size_t scd_name_topk_workspace_bytes(int64_t N, int64_t V, int k);
+/* Introspection (no reference counterpart): the work partition scd_name_topk uses for (N, V, k) on the current device -
+ * out[0] = 256-row blocks, out[1] = vocabulary tiles per sweep, out[2] = row blocks that sweep the whole vocabulary as
+ * one work item (whole waves), out[3] = vocabulary chunks the remaining (tail-wave) row blocks are split into,
+ * out[4] = tiles per chunk, out[5] = CTA pairs launched.  Host-only. */
+SCD_API int scd_name_topk_plan(int64_t N, int64_t V, int k, int32_t* out6 /* host */);
 SCD_API int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, int64_t V, float scale, int k,
                   int want_softmax, int64_t idx_offset, float* vals, int64_t* idx,
                   float* row_max, float* row_sumexp, void* ws, size_t ws_bytes, scd_stream_t stream);

@@ -33,6 +33,7 @@ SIGNATURES = {
     'scd_cast_bf16': (_int, [_vp, _i64, _vp, _vp]),
     'scd_gather_rows_bf16': (_int, [_vp, _vp, _int, _int, _i64, _vp, _vp]),
     'scd_name_topk_workspace_bytes': (_sz, [_i64, _i64, _int]),
+    'scd_name_topk_plan': (_int, [_i64, _i64, _int, _vp]),
     'scd_name_topk': (_int, [_vp, _i64, _int, _vp, _i64, _f32, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'scd_topk_merge': (_int, [_vp, _vp, _vp, _vp, _int, _i64, _int, _f32, _int, _vp, _vp, _vp]),
     'scd_vote_workspace_bytes': (_sz, [_i64, _int]),

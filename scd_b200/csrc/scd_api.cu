@@ -467,6 +467,14 @@ size_t scd_name_topk_workspace_bytes(int64_t N, int64_t V, int k) {
   return pl.bytes;
 }
 
+int scd_name_topk_plan(int64_t N, int64_t V, int k, int32_t* out6) {
+  NamePlan pl;
+  if (!out6 || N <= 0 || V <= 0 || !plan_naming(N, V, k, &pl)) return fail("scd_name_topk_plan: bad arguments");
+  out6[0] = pl.n_row_blocks; out6[1] = pl.tiles_total; out6[2] = pl.n_full_rb;
+  out6[3] = pl.n_vsplit; out6[4] = pl.tiles_per_chunk; out6[5] = pl.n_pairs;
+  return 0;
+}
+
 int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, int64_t V, float scale, int k, int want_softmax,
                   int64_t idx_offset, float* vals, int64_t* idx, float* row_max, float* row_sumexp, void* ws, size_t ws_bytes,
                   scd_stream_t stream) {
