@@ -4,14 +4,23 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C2]
 
-* default arm: the B200 path.  `value` = ms per round with all inputs resident in HBM (CUDA events, max
-  over ranks); `e2e` = the same round through the public Python API with HOST (pinned) buffers, H2D/D2H
-  inside the timed region; `roofline` = the dominant kernel (fused scoring/top-k, tensor-core bound)
-  against MEASURED_PEAKS.json; `cpu_baseline` = the oracle (a port of the reference's PyTorch path) timed on
-  this box's host cores on a bounded row sample (N=1 / rank 0 only).
-* N > 1 (launched by torch.distributed.run, one rank per GPU): STRONG scaling of the same workload - rows
-  block-sharded for k-means (one packed NCCL all-reduce per iteration), vocabulary column-sharded for naming
-  (local fused top-k, all-gather, k-way merge), vote replicated.
+* default arm: the B200 path.  `value` = ms per round of the HEADLINE config (C2, the 1-GPU configuration the metric is
+  quoted on) with all inputs resident in HBM (CUDA events, max over ranks); `e2e` = the same round through the public
+  Python API with HOST (pinned) buffers, H2D/D2H inside the timed region; `roofline` = the dominant kernel (fused
+  scoring/top-k, tensor-core bound) against MEASURED_PEAKS.json; `cpu_baseline` = the oracle (a port of the reference's
+  PyTorch path) timed on this box's host cores on a bounded row sample; `torch_cuda_baseline` = the reference's own
+  PyTorch expressions run on CUDA tensors on the same GPU (N=1 / rank 0 only).
+* N > 1 (launched by torch.distributed.run, one rank per GPU): STRONG scaling of the same workload.  Image rows are
+  block-sharded for BOTH contractions - k-means (one packed NCCL all-reduce of [K*D sums | K counts | inertia] per
+  iteration) and naming (vocabulary replicated, no exchange) - then each rank packs [label, top-k names] int32 records,
+  ONE all-gather replicates them and the exact vote runs on every rank.  `--naming-shard vocab` switches naming to the
+  vocabulary-column-sharded scheme of BASELINE.json configs[3] (all rows x V/N columns per rank, all-gather of the
+  [N, k] lists, k-way merge kernel); `--vocab-ways G` makes it a (N/G) x G rows x vocabulary process grid.
+* every line also carries (unless --no-extra): `c5` - the 1.28M x 768, K=1000, V=100k stress config (configs[4]) on
+  the same N GPUs, rows sharded; `c4_vocab_shard` - the V=82k sweep config (configs[3]) with the vocabulary
+  column-sharded, next to the same config row-sharded; and `parity` - sha1 hashes of labels / top-k indices / voted
+  names of one round from the initial centroids, and whether the N-rank result equals a 1-rank recomputation of the
+  whole workload on rank 0 (`equals_n1`).
 * --impl reference: the reference's own CPU implementation of the path (the oracle port - the reference is
   Python/PyTorch, there is nothing to compile into oracle/_ref) with all host threads, on a bounded sample of
   the same workload, extrapolated linearly in rows.  Rank 0 only.
@@ -19,6 +28,7 @@
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -33,6 +43,7 @@ import torch
 
 METRIC = 'ms per naming round (k-means iter + vocab top-k + vote)'
 CPU_SAMPLE_ROWS = int(os.environ.get('SCD_BENCH_CPU_ROWS', '8192'))      # rows of the bounded CPU sample (tests shrink it)
+TOPK, NUM_COMMON = 5, 20
 
 
 # ------------------------------------------------------------------------------------------ helpers
@@ -120,6 +131,11 @@ def physical_gpu_index(local_rank):
     return local_rank
 
 
+def sha(t: torch.Tensor) -> str:
+    """sha1 of a tensor's bytes (moved to the host), first 16 hex digits."""
+    return hashlib.sha1(t.detach().contiguous().cpu().numpy().tobytes()).hexdigest()[:16]
+
+
 # ------------------------------------------------------------------------------------------ CPU legs
 _CPU_DATA = {}
 
@@ -154,116 +170,360 @@ def cpu_round_ms(cfg, sample_rows, threads, repeats=2):
     return best['total'] * 1e3 * scale, detail, n
 
 
+# ------------------------------------------------------------------------------------------ reference torch path on CUDA
+def torch_cuda_round(X, Xc, W, C, k, dtype):
+    """The reference's OWN PyTorch expressions on CUDA tensors (what a user of the reference runs on this GPU),
+    restated here - bench.py may not import oracle/ outside the CPU legs:
+      * E-step   local_utils/faster_mix_k_means_pytorch.py:177-212 pairwise_distance in 1024-row batches (broadcast
+                 (A - B) ** 2 .sum(-1); the result buffer is on the CPU there, :197 - kept on the device here, which
+                 only helps the baseline), torch.min :59, mindist.sum() :60
+      * M-step   :61-64 per-cluster nonzero -> index_select -> mean
+      * naming   main_ptsup.py:538-543 per 1024-row batch: 100. * feats @ zeroshot_weights, topk(5) twice
+      * vote     main_unsup.py:575-582 Counter per cluster on the host (after ONE copy of the indices, not K)
+    Returns (labels, idx, per-part CUDA-event ms)."""
+    from collections import Counter
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    n = X.shape[0]
+    ev[0].record()
+    dist = torch.empty(n, k, device=X.device)
+    for lo in range(0, n, 1024):
+        a = X[lo:lo + 1024].unsqueeze(1)
+        dist[lo:lo + 1024] = ((a - C.unsqueeze(0)) ** 2.0).sum(dim=-1)
+    mindist, labels = torch.min(dist, dim=1)
+    inertia = mindist.sum()
+    centers = C.clone()
+    for idx in range(k):
+        selected = torch.nonzero(labels == idx).squeeze()
+        selected = torch.index_select(X, 0, selected)
+        centers[idx] = selected.mean(dim=0)
+    ev[1].record()
+    feats, Wd = Xc.to(dtype), W.to(dtype)
+    top_i, top_v = [], []
+    for lo in range(0, n, 1024):
+        logits = 100. * feats[lo:lo + 1024] @ Wd
+        top_v.append(logits.topk(TOPK, 1, True, True)[0])
+        top_i.append(logits.topk(TOPK, 1, True, True)[1])
+    idx5 = torch.cat(top_i)
+    torch.cat(top_v)
+    ev[2].record()
+    idx_h, lab_h = idx5.cpu().numpy(), labels.cpu().numpy()
+    t0 = time.perf_counter()
+    for c in range(k):
+        Counter(x for x in idx_h[lab_h == c, :TOPK].reshape(-1)).most_common(NUM_COMMON)
+    vote_ms = (time.perf_counter() - t0) * 1e3
+    ev[3].record()
+    torch.cuda.synchronize()
+    float(inertia)
+    return labels, idx5, dict(kmeans=ev[0].elapsed_time(ev[1]), naming=ev[1].elapsed_time(ev[2]), vote=vote_ms)
+
+
+def torch_cuda_baseline(rnd, repeats=3):
+    """Times `torch_cuda_round` on the headline workload, inputs resident in HBM (same tensors the B200 arm uses)."""
+    cfg = rnd.cfg
+    X, C = rnd.X, rnd.C0
+    Xc32 = rnd.Xc.float()
+    W32 = rnd.vocab.Wt.float().t().contiguous()                   # the reference's [D, V] layout
+    out = {}
+    for name, dtype in (('bf16', torch.bfloat16), ('fp32', torch.float32)):
+        best = None
+        for _ in range(repeats):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, _, parts = torch_cuda_round(X, Xc32, W32, C, cfg.k, dtype)
+            total = (time.perf_counter() - t0) * 1e3
+            if best is None or total < best['total']:
+                best = dict(total=total, **parts)
+        out[name] = {k: round(v, 3) for k, v in best.items()}
+    return dict(value=out['bf16']['total'], unit='ms', gemm_dtype='bf16 (cuBLAS); fp32 variant beside it', split_ms=out,
+                what='reference PyTorch expressions on CUDA tensors (1024-row batches, [1024, V] logits in HBM, topk twice, '
+                     'K-launch M-step, host Counter vote), wall clock incl. its own host syncs, best of %d' % repeats)
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
+def device_data(cfg, device, d):
+    """Synthetic inputs of one config generated ON THE DEVICE (the extra C4 / C5 blocks: 1.28M x 768 rows would take
+    minutes with the host generator): unit-norm fp32 image features with K-class structure, bf16 CLIP-like features,
+    bf16-rounded unit-norm vocabulary [d, V], centroids = K distinct rows.  Deterministic for a given (config, GPU type)."""
+    g = torch.Generator(device=device).manual_seed(cfg.seed)
+    mu = torch.randn(cfg.k, d, generator=g, device=device)
+    mu = mu / mu.norm(dim=1, keepdim=True)
+    y = torch.randint(0, cfg.k, (cfg.n,), generator=g, device=device)
+    X = torch.empty(cfg.n, d, device=device)
+    Xc = torch.empty(cfg.n, d, dtype=torch.bfloat16, device=device)
+    mu2 = torch.randn(cfg.k, d, generator=g, device=device)
+    mu2 = mu2 / mu2.norm(dim=1, keepdim=True)
+    for lo in range(0, cfg.n, 131072):
+        hi = min(lo + 131072, cfg.n)
+        x = torch.randn(hi - lo, d, generator=g, device=device) + 4.0 * mu[y[lo:hi]]
+        X[lo:hi] = x / x.norm(dim=1, keepdim=True)
+        x = torch.randn(hi - lo, d, generator=g, device=device) + 4.0 * mu2[y[lo:hi]]
+        Xc[lo:hi] = (x / x.norm(dim=1, keepdim=True)).to(torch.bfloat16)
+    W = torch.empty(d, cfg.v, dtype=torch.bfloat16, device=device)
+    for lo in range(0, cfg.v, 16384):
+        hi = min(lo + 16384, cfg.v)
+        w = torch.randn(hi - lo, d, generator=g, device=device)
+        W[:, lo:hi] = (w / w.norm(dim=1, keepdim=True)).to(torch.bfloat16).t()
+    pick = torch.randperm(cfg.n, generator=g, device=device)[:cfg.k]
+    return dict(X=X, Xc=Xc, W=W, C0=X[pick].clone())
+
+
 class Round:
     """Device-resident state of one rank and the launches of one naming round.
 
-    N = 1: everything local.  N > 1: image rows block-sharded over the ranks for BOTH contractions - k-means
-    (one packed NCCL all-reduce of [K*D sums | K counts | inertia] per iteration) and naming (every rank
-    holds the whole vocabulary, 32 MB, so its rows' top-k needs no exchange) - then the per-row results
-    (labels, top-k name indices; N*48 bytes in total) are all-gathered and the vote runs replicated.
-    `naming_shard='vocab'` switches naming to the vocabulary-column-sharded scheme (all rows x V/N columns per
-    rank, all-gather of [N, k] lists, k-way merge kernel)."""
+    N = 1: everything local.  N > 1: image rows block-sharded over the ranks for BOTH contractions - k-means (one
+    packed NCCL all-reduce of [K*D sums | K counts | inertia] per iteration) and naming (every rank holds the whole
+    vocabulary, so its rows' top-k needs no exchange) - then the rank's [label, top-k names] int32 records (24 bytes
+    per row) are all-gathered once and the exact vote runs replicated on the gathered records.
+    `naming_shard='vocab'`: a (world / vocab_ways) x vocab_ways process grid - a rank scores the rows of its row group
+    against its vocabulary-column shard, the partial [rows, k] lists are all-gathered inside the group and merged by
+    the k-way merge kernel (vocab_ways = world: every rank scores all rows, BASELINE.json configs[3]).
 
-    def __init__(self, cfg, rank, world, group, naming_shard='rows'):
+    Successive rounds are successive k-means iterations: the centres ping-pong between two buffers and
+    scd_finalize_centers leaves the next E-step's operands in place, exactly like K_Means._lloyd."""
+
+    def __init__(self, cfg, rank, world, group, naming_shard='rows', vocab_ways=None, data=None, host_data=None):
         from scd_b200 import dist as sdist, kmeans, naming, synth
         self.cfg, self.rank, self.world, self.group = cfg, rank, world, group
         self.kmeans, self.naming, self.sdist = kmeans, naming, sdist
         self.naming_shard = naming_shard if world > 1 else 'rows'
-        data = synth.make(cfg)
-        self.host = data
         dev = torch.device('cuda')
+        d = synth.D
+        self.host = host_data
+        if data is None:
+            data = {k: host_data[k] for k in ('X', 'Xc', 'W', 'C0')}
         self.row_lo, self.row_hi = sdist.shard_bounds(cfg.n, world, rank)
         n_local = self.row_hi - self.row_lo
-        self.X = data['X'][self.row_lo:self.row_hi].to(dev).contiguous()
-        self.C = data['C0'].to(dev).contiguous()
-        self.C_new = torch.empty_like(self.C)
+        own = lambda t: t.clone() if t.is_cuda else t.to(dev).contiguous()       # never keep a view of the whole config alive
+        self.X = own(data['X'][self.row_lo:self.row_hi])
+        self.C0 = data['C0'].to(dev).contiguous()
+        self.C = [self.C0.clone(), torch.empty_like(self.C0)]
+        self.cur = 0
         self.inertia = torch.zeros(1, dtype=torch.float64, device=dev)
-        self.mstep = kmeans._MStep(n_local, synth.D, cfg.k, dev)
+        self.mstep = kmeans._MStep(n_local, d, cfg.k, dev)
+        self.estep = kmeans._EStep(cfg.k, d, dev)
         self.km = kmeans.K_Means(k=cfg.k, process_group=group if world > 1 else None)
-        if world > 1:
-            self.g_labels = sdist.RowGather(cfg.n, (), torch.int64, dev, group)
-            self.labels = self.g_labels.local
-        else:
-            self.g_labels = None
-            self.labels = torch.empty(n_local, dtype=torch.int64, device=dev)
+        self.labels = torch.empty(n_local, dtype=torch.int64, device=dev)
+        self.g_rec = sdist.RowGather(cfg.n, (1 + TOPK,), torch.int32, dev, group) if world > 1 else None
+        self.subgroup = None
         if self.naming_shard == 'rows':
-            self.col_lo, self.col_hi = 0, cfg.v
-            self.Xc = naming._feats_bf16(data['Xc'][self.row_lo:self.row_hi])
+            self.name_rows = (self.row_lo, self.row_hi)
+            self.Xc = naming._feats_bf16(own(data['Xc'][self.row_lo:self.row_hi]))
             self.vocab = naming.Vocabulary(data['W'].to(dev))
-            if world > 1:
-                self.g_idx = sdist.RowGather(cfg.n, (5,), torch.int64, dev, group)
-                self.topk = naming.TopKPlan(n_local, cfg.v, 5, dev, idx_out=self.g_idx.local)
-            else:
-                self.g_idx = None
-                self.topk = naming.TopKPlan(n_local, cfg.v, 5, dev)
-            self.name_flops = 2.0 * n_local * cfg.v * synth.D
+            self.topk = naming.TopKPlan(n_local, cfg.v, TOPK, dev)
+            self.name_flops = 2.0 * n_local * cfg.v * d
         else:
-            self.col_lo, self.col_hi = sdist.shard_bounds(cfg.v, world, rank)
-            self.Xc = naming._feats_bf16(data['Xc'])
+            import torch.distributed as dist
+            ways = world if not vocab_ways else int(vocab_ways)
+            row_groups = world // ways
+            rg, vg = sdist.grid_2d(world, rank, ways)
+            # every rank must create every subgroup, in the same order
+            for q in range(row_groups):
+                ranks = list(range(q * ways, (q + 1) * ways))
+                grp = dist.new_group(ranks=ranks) if ways < world else group
+                if q == rg:
+                    self.subgroup = grp
+            self.ways, self.vg = ways, vg
+            # a row group's rows = the union of the k-means shards of its ranks
+            lo, hi = sdist.shard_bounds(cfg.n, world, rg * ways)[0], sdist.shard_bounds(cfg.n, world, rg * ways + ways - 1)[1]
+            self.name_rows = (lo, hi)
+            self.col_lo, self.col_hi = sdist.shard_bounds(cfg.v, ways, vg)
+            self.Xc = naming._feats_bf16(own(data['Xc'][lo:hi]))
             self.vocab = naming.Vocabulary(data['W'][:, self.col_lo:self.col_hi].to(dev), col_offset=self.col_lo)
-            self.g_idx = None
-            self.topk = naming.TopKPlan(cfg.n, self.col_hi - self.col_lo, 5, dev, want_stats=True)
-            self.name_flops = 2.0 * cfg.n * (self.col_hi - self.col_lo) * synth.D
-        self.vote_plan = naming.VotePlan(cfg.n, cfg.k, 20, dev)
+            self.topk = naming.TopKPlan(hi - lo, self.col_hi - self.col_lo, TOPK, dev, want_stats=True)
+            self.name_flops = 2.0 * (hi - lo) * (self.col_hi - self.col_lo) * d
+            # every rank of the group ends up with the merged lists of all the group's rows; its vote records take
+            # the slice that belongs to its own k-means rows
+        self.vote_plan = naming.VotePlan(cfg.n, cfg.k, NUM_COMMON, dev, k_used=TOPK)
         self.launches_per_round = 0
-        self.ev_name = None
-        self.graph = None
+        self.graphs = None
+        self.last = None
 
+    # -- one round; `ev_name`: optional (start, stop) events around the scoring/top-k launches
     def run(self, ev_name=None):
-        cfg, km, nm = self.cfg, self.kmeans, self.naming
+        cfg, nm = self.cfg, self.naming
         launches = 0
-        # ---- k-means iteration: E-step, M-step sums, (all-reduce), divide + centre shift
+        c_old, c_new = self.C[self.cur], self.C[self.cur ^ 1]
+        # ---- k-means iteration: E-step, M-step sums, (all-reduce), divide (+ next E-step's operands)
         self.inertia.zero_()
-        km._estep(self.X, self.C, self.labels, self.inertia); launches += 2           # centroid split + E-step
-        self.mstep.sums_counts(self.X, self.labels); launches += 4                    # hist, scan, scatter, segment sum
+        ready = self.estep.ready_for == c_old.data_ptr()
+        self.estep.run(self.X, c_old, self.labels, self.inertia); launches += 1 if ready else 2     # (centroid split +) E-step
+        self.mstep.sums_counts(self.X, self.labels); launches += 3                    # hist+scan, scatter, segment sum
         counts_f = self.km._allreduce(self.mstep, self.inertia)
         launches += 1 if counts_f is not None else 0                                  # pack (the all-reduce is NCCL's)
-        self.mstep.finalize(self.C, self.C_new, counts_f); launches += 2
+        self.mstep.finalize(c_old, c_new, counts_f, estep=self.estep, shift=False); launches += 1
         # ---- full-vocabulary scoring + per-image top-5
         if ev_name is not None:
             ev_name[0].record()
         if self.naming_shard == 'rows':
             vals, idx, _, _ = self.topk.run(self.Xc, self.vocab, False); launches += 2
         else:
-            vals, idx = self.sdist.sharded_score_topk(self.Xc, self.vocab, 5, False, self.group, plan=self.topk); launches += 3
+            vals, idx = self.sdist.sharded_score_topk(self.Xc, self.vocab, TOPK, False, self.subgroup, plan=self.topk); launches += 3
+            lo = self.row_lo - self.name_rows[0]
+            vals, idx = vals[lo:lo + (self.row_hi - self.row_lo)], idx[lo:lo + (self.row_hi - self.row_lo)]
         if ev_name is not None:
             ev_name[1].record()
         # ---- per-cluster vote over all rows
         if self.world == 1:
-            out = nm.vote_device(idx, None, cfg.k, 5, 20, plan=self.vote_plan, presorted=self.mstep); launches += 1
+            out = nm.vote_device(idx, None, cfg.k, TOPK, NUM_COMMON, plan=self.vote_plan, presorted=self.mstep); launches += 1
         else:
-            labels_all = self.g_labels.gather()
-            idx_all = self.g_idx.gather() if self.g_idx is not None else idx
-            out = nm.vote_device(idx_all, labels_all, cfg.k, 5, 20, plan=self.vote_plan); launches += 4
+            out = self.sdist.sharded_vote(self.labels, idx, TOPK, cfg.k, NUM_COMMON, self.g_rec, plan=self.vote_plan); launches += 4
+        self.cur ^= 1
         self.launches_per_round = launches
         self.last = (vals, idx, out)
         return out
 
+    def reset(self):
+        """Back to the initial centroids (the parity round starts from them on every N)."""
+        self.C[0].copy_(self.C0)
+        self.cur = 0
+        self.estep.ready_for = None
+
     def capture(self):
-        """Record one round into a CUDA graph (launch-bound at N > 1: ~15 launches of 5-400 us each)."""
+        """Record two rounds (centres C[0] -> C[1] and C[1] -> C[0]) into CUDA graphs: the round is launch-bound at N > 1."""
         try:
-            g = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self.run()
+                if self.cur != 0:
+                    self.run()
+                self.run(); self.run()                       # steady state: the operands of C[0] are in the E-step workspace
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            with torch.cuda.graph(g, stream=side):
-                self.run()
-            self.graph = g
+            graphs = []
+            for _ in range(2):                               # graphs[i] is the round that starts from C[i]
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    self.run()
+                graphs.append(g)
+            self.graphs = graphs
         except Exception as e:                                  # eager launches are always available
             sys.stderr.write(f'[bench] CUDA graph capture failed, timing eager launches: {e}\n')
-            self.graph = None
+            self.graphs = None
             torch.cuda.synchronize()
-        return self.graph is not None
+        return self.graphs is not None
 
     def step(self):
-        if self.graph is not None:
-            self.graph.replay()
+        if self.graphs is not None:
+            self.graphs[self.cur].replay()
+            self.cur ^= 1
+            self.estep.ready_for = self.C[self.cur].data_ptr()
         else:
             self.run()
+
+    def drop_graphs(self):
+        self.graphs = None
+
+
+def measure(rnd, steps, warmup, world, group, use_graph, sampler=None):
+    """Warm up, (capture,) time `steps` rounds with CUDA events between barriers, then time the scoring/top-k launches
+    of a few eager rounds.  Returns (ms_per_step, naming_ms, graphed) as the max over ranks."""
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=group)
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        rnd.run()
+    barrier()
+    graphed = rnd.capture() if use_graph else False
+    if world > 1:                                   # every rank must take the same path (collectives inside)
+        import torch.distributed as dist
+        flag = torch.tensor([1 if graphed else 0], device='cuda')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if not bool(flag.item()):
+            rnd.drop_graphs()
+            graphed = False
+    if graphed:
+        for _ in range(2):
+            rnd.step()
+    barrier()
+    if sampler is not None:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        rnd.step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    # the dominant kernel, timed live with events around its launch (eager launches, same stream, same inputs)
+    n_k = max(3, min(steps, 20))
+    name_evs = []
+    for _ in range(n_k):
+        evs = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        rnd.run(ev_name=evs)
+        name_evs.append(evs)
+    barrier()
+    name_ms = float(np.mean([a.elapsed_time(b) for a, b in name_evs]))
+    t = torch.tensor([ms_total, name_ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t[0]) / steps, float(t[1]), graphed
+
+
+def parity_block(rnd, data, world, group):
+    """One round from the initial centroids on the N ranks; hashes of the gathered labels / top-k indices / voted names;
+    on rank 0 the same round recomputed on ONE GPU over all rows (`equals_n1`).  At N = 1 the hashes are the reference
+    values a reader compares the N > 1 lines with."""
+    from scd_b200 import kmeans, naming
+    cfg = rnd.cfg
+    rnd.reset()
+    names, counts, _, _, ovf = rnd.run()
+    vals, idx, _ = rnd.last
+    torch.cuda.synchronize()
+    if world > 1:
+        rec = rnd.g_rec.full                                     # gathered [N, 1 + k] records of this very round
+        labels_all, idx_all = rec[:, 0].long(), rec[:, 1:].long()
+    else:
+        labels_all, idx_all = rnd.labels, idx
+    out = dict(labels_sha=sha(labels_all), topk_idx_sha=sha(idx_all), voted_sha=sha(names), vote_counts_sha=sha(counts),
+               vote_overflow=int(ovf.item()), rows=int(labels_all.shape[0]))
+    if world > 1 and rnd.rank == 0:
+        dev = torch.device('cuda')
+        X = data['X'].to(dev)
+        lab1 = torch.empty(cfg.n, dtype=torch.int64, device=dev)
+        kmeans._estep(X, rnd.C0, lab1, None)
+        del X
+        vocab = naming.Vocabulary(data['W'].to(dev))
+        _, idx1 = naming.score_topk(naming._feats_bf16(data['Xc']), vocab, k=TOPK, softmax=False)
+        names1, counts1, _, _, _ = naming.vote_device(idx1, lab1, cfg.k, TOPK, NUM_COMMON)
+        torch.cuda.synchronize()
+        out.update(n1=dict(labels_sha=sha(lab1), topk_idx_sha=sha(idx1), voted_sha=sha(names1), vote_counts_sha=sha(counts1)),
+                   labels_mismatch=int((lab1 != labels_all).sum().item()), topk_idx_mismatch=int((idx1 != idx_all).sum().item()),
+                   voted_mismatch=int((names1 != names).sum().item()))
+        out['equals_n1'] = bool(out['labels_mismatch'] == 0 and out['topk_idx_mismatch'] == 0 and out['voted_mismatch'] == 0 and
+                                torch.equal(counts1, counts))
+    return out
+
+
+def extra_block(name, rank, world, group, peaks, steps, naming_shard, vocab_ways=None):
+    """Timing + parity of one of the other BASELINE.json configs on the same N GPUs (device-generated inputs)."""
+    from scd_b200 import synth
+    cfg = synth.CONFIGS[name]
+    t0 = time.time()
+    data = device_data(cfg, torch.device('cuda'), synth.D)
+    rnd = Round(cfg, rank, world, group, naming_shard, vocab_ways, data=data)
+    if world == 1:
+        data_keep = None
+    else:
+        data_keep = data if rank == 0 else None
+    del data
+    ms, name_ms, graphed = measure(rnd, steps, 3, world, group, use_graph=True)
+    rnd.drop_graphs()
+    par = parity_block(rnd, data_keep, world, group)
+    achieved = rnd.name_flops / (name_ms * 1e-3) / 1e12
+    blk = dict(workload=f'{cfg.name}: {cfg.n}x{synth.D} image features, K={cfg.k}, V={cfg.v} names, top-{TOPK}, vote top-{NUM_COMMON}',
+               sharding=('rows' if rnd.naming_shard == 'rows' else f'{world // rnd.ways} row groups x {rnd.ways} vocabulary shards'),
+               ms_per_step=round(ms, 4), naming_ms=round(name_ms, 4), rest_ms=round(ms - name_ms, 4), steps=steps,
+               kernel_tflops=round(achieved, 1), kernel_frac=round(achieved / peaks['tflops'], 4),
+               kernel_frac_of_sustained=round(achieved / peaks['tflops_sustained'], 4),
+               launch_mode='cuda-graph replay' if graphed else 'eager', data='synthetic, generated on the device',
+               parity=par, wall_s=round(time.time() - t0, 1))
+    del rnd, data_keep
+    torch.cuda.empty_cache()
+    return blk
 
 
 def e2e_round(cfg, host, vocab, pinned):
@@ -275,13 +535,26 @@ def e2e_round(cfg, host, vocab, pinned):
     km = kmeans.K_Means(k=cfg.k, max_iterations=1, n_init=1)
     labels = torch.empty(cfg.n, dtype=torch.int64, device='cuda')
     best_labels, inertia, centers, _ = km._lloyd(X, X, labels, 0, C)
-    vals, idx = naming.score_topk(Xc, vocab, k=5, softmax=False)
-    names, counts, distinct, rows, ovf = naming.vote_device(idx, best_labels, cfg.k, 5, 20)
+    vals, idx = naming.score_topk(Xc, vocab, k=TOPK, softmax=False)
+    names, counts, distinct, rows, ovf = naming.vote_device(idx, best_labels, cfg.k, TOPK, NUM_COMMON)
     res = [t.to('cpu', non_blocking=True) for t in (best_labels, centers, vals, idx, names, counts)]
     torch.cuda.synchronize()
     h2d = X.numel() * 4 + C.numel() * 4 + Xc.numel() * 4
     d2h = sum(t.numel() * t.element_size() for t in res) + 16
     return h2d, d2h
+
+
+def h2d_gbs(pinned_t):
+    """Measured pinned host -> device copy bandwidth (GB/s) of this box: the floor of `e2e` is its bytes over this."""
+    dst = torch.empty_like(pinned_t, device='cuda')
+    dst.copy_(pinned_t, non_blocking=True)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    dst.copy_(pinned_t, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    return pinned_t.numel() * pinned_t.element_size() / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
 
 
 def main():
@@ -293,10 +566,14 @@ def main():
     ap.add_argument('--config', default='C2')
     ap.add_argument('--naming-shard', default='rows', choices=['rows', 'vocab'],
                     help='N > 1: how the scoring/top-k is partitioned (rows: no exchange; vocab: all-gather + k-way merge)')
+    ap.add_argument('--vocab-ways', type=int, default=0, help='with --naming-shard vocab: vocabulary shards per row group (default: N)')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of CUDA-graph replays')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-torch-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-clocks', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the c5 / c4_vocab_shard / sustained blocks')
+    ap.add_argument('--extra-steps', type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
@@ -311,9 +588,11 @@ def main():
         par = 'single GPU'
     elif args.naming_shard == 'rows':
         par = (f'rows/{world} for k-means (packed NCCL all-reduce of sums+counts+inertia) and for naming (vocabulary replicated, '
-               f'no exchange); labels + top-k indices all-gathered, vote replicated')
+               f'no exchange); [label, top-k names] int32 records all-gathered once, exact vote replicated')
     else:
-        par = f'rows/{world} (k-means, all-reduce) x vocab/{world} (naming, all-gather + k-way merge); vote replicated'
+        ways = args.vocab_ways or world
+        par = (f'rows/{world} (k-means, all-reduce) x naming on a {world // ways} x {ways} rows x vocabulary grid (all-gather of '
+               f'[rows, k] lists inside a row group + k-way merge); vote records all-gathered once, exact vote replicated')
     config = dict(workload=f'{cfg.name}: {cfg.n}x{synth.D} image features, K={cfg.k}, V={cfg.v} names, top-5, vote top-20',
                   n=cfg.n, d=synth.D, k=cfg.k, v=cfg.v, topk=5,
                   l2=f'inputs ({feat_mb:.0f} MB features + {voc_mb:.0f} MB vocabulary) exceed the 126 MB L2', parallelism=par)
@@ -333,7 +612,8 @@ def main():
         print(json.dumps(dict(impl='reference', metric=METRIC, value=round(v, 1), unit='ms', n_gpus=args.gpus, steps=args.steps,
                               warmup=args.warmup, ms_per_step=round(v, 1), higher_is_better=False, scaling='strong',
                               vs_baseline=None, dtype='f32', data='synthetic', config=config,
-                              cpu_baseline=dict(value=round(v, 1), unit='ms', cores=threads, kind='port', sample=sample, split_ms=detail),
+                              cpu_baseline=dict(value=round(v, 1), unit='ms', cores=threads, kind='port', sample=sample, split_ms=detail,
+                                                reference_checkout_present=os.path.isdir('/root/reference')),
                               e2e=dict(value=round(v, 1), unit='ms', h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
         return 0
 
@@ -351,55 +631,15 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
         group = dist.group.WORLD
     peaks = load_peaks()
-    rnd = Round(cfg, rank, world, group, args.naming_shard)
+    host = synth.make(cfg)
+    rnd = Round(cfg, rank, world, group, args.naming_shard, args.vocab_ways or None, host_data=host)
 
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier(group=group)
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        rnd.run()
-    barrier()
-    graphed = False if args.no_graph else rnd.capture()
-    if world > 1:                                   # every rank must take the same path (collectives inside)
-        import torch.distributed as dist
-        flag = torch.tensor([1 if graphed else 0], device='cuda')
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        if not bool(flag.item()):
-            rnd.graph, graphed = None, False
-    if graphed:
-        for _ in range(2):
-            rnd.step()
-    barrier()
     sampler = ClockSampler(physical_gpu_index(local_rank), enabled=not args.no_clocks)
-    barrier()
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        rnd.step()
-    ev1.record()
-    barrier()
+    ms_per_step, name_ms, graphed = measure(rnd, args.steps, args.warmup, world, group, not args.no_graph, sampler)
     clocks = sampler.result()
-    ms_total = ev0.elapsed_time(ev1)
-
-    # the dominant kernel, timed live with events around its launch (eager launches, same stream, same inputs)
-    n_k = max(3, min(args.steps, 20))
-    name_evs = []
-    for _ in range(n_k):
-        evs = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        rnd.run(ev_name=evs)
-        name_evs.append(evs)
-    barrier()
-    name_ms = float(np.mean([a.elapsed_time(b) for a, b in name_evs]))
-    t = torch.tensor([ms_total, name_ms], dtype=torch.float64, device='cuda')
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-    ms_per_step = float(t[0]) / args.steps
-    name_ms = float(t[1])
+    launches_per_round = rnd.launches_per_round
+    rnd.drop_graphs()
+    parity = parity_block(rnd, host, world, group)
 
     # roofline of the dominant kernel: fused scoring/top-k (tensor-core bound); algorithmic flops = 2 * rows * cols * D of this rank
     flops = rnd.name_flops
@@ -414,42 +654,94 @@ def main():
                     peak_source=f"{peaks['source']} bf16 burst (MEASURED_PEAKS.json); sustained figure: {peaks['tflops_sustained']}",
                     kernel_ms=round(name_ms, 4), flops_per_launch=flops)
 
+    # sustained regime: the same graph replayed back to back for >= 2 s (power-capped clocks), against the sustained peak
+    sustained = None
+    if not args.no_extra and world == 1:
+        rnd.capture()
+        n_rep = max(50, int(2200.0 / max(ms_per_step, 0.05)))
+        s2 = ClockSampler(physical_gpu_index(local_rank), enabled=not args.no_clocks)
+        torch.cuda.synchronize()
+        s2.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_rep):
+            rnd.step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_sus = e0.elapsed_time(e1) / n_rep
+        ck = s2.result()
+        est_name = ms_sus - (ms_per_step - name_ms)
+        sustained = dict(rounds=n_rep, seconds=round(ms_sus * n_rep / 1e3, 2), ms_per_step=round(ms_sus, 4),
+                         est_kernel_tflops=round(flops / (est_name * 1e-3) / 1e12, 1),
+                         est_kernel_frac_of_sustained_peak=round(flops / (est_name * 1e-3) / 1e12 / peaks['tflops_sustained'], 4),
+                         note='kernel time estimated as the sustained round minus the burst-measured rest of the round', clocks=ck)
+        rnd.drop_graphs()
+
     e2e = None
     cpu_baseline = None
+    torch_base = None
     if rank == 0 and world == 1 and not args.no_e2e:
-        pinned = {k: rnd.host[k].pin_memory() for k in ('X', 'Xc', 'C0')}
+        pinned = {k: host[k].pin_memory() for k in ('X', 'Xc', 'C0')}
+        gbs = h2d_gbs(pinned['X'])
         for _ in range(2):
-            h2d, d2h = e2e_round(cfg, rnd.host, rnd.vocab, pinned)
+            h2d, d2h = e2e_round(cfg, host, rnd.vocab, pinned)
         torch.cuda.synchronize()
         n_e2e = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            h2d, d2h = e2e_round(cfg, rnd.host, rnd.vocab, pinned)
+            h2d, d2h = e2e_round(cfg, host, rnd.vocab, pinned)
         torch.cuda.synchronize()
         e2e = dict(value=round((time.perf_counter() - t0) * 1e3 / n_e2e, 3), unit='ms', h2d_bytes_per_step=int(h2d),
-                   d2h_bytes_per_step=int(d2h), api='K_Means._lloyd(1 iter) + naming.score_topk (chunked upload under the kernel) + naming.vote_device from pinned host tensors')
+                   d2h_bytes_per_step=int(d2h), h2d_gbs_measured=round(gbs, 1), pcie_floor_ms=round(h2d / gbs / 1e6, 3),
+                   api='K_Means._lloyd(1 iter) + naming.score_topk (chunked upload under the kernel) + naming.vote_device from pinned host tensors')
+        del pinned
     elif world > 1:
         e2e = dict(value=None, unit='ms', h2d_bytes_per_step=0, d2h_bytes_per_step=0, note='measured at N=1 only')
+    if rank == 0 and world == 1 and not args.no_torch_baseline:
+        try:
+            torch_base = torch_cuda_baseline(rnd)
+        except Exception as e:                                     # a baseline, never a reason to lose the line
+            torch_base = dict(value=None, error=str(e)[:200])
+        torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, detail, n_s = cpu_round_ms(cfg, CPU_SAMPLE_ROWS, threads, repeats=2)
         cpu_baseline = dict(value=round(v, 1), unit='ms', cores=threads, kind='port', split_ms=detail,
+                            reference_checkout_present=os.path.isdir('/root/reference'),
                             sample=f'{n_s} of {cfg.n} rows (all {cfg.k} centroids, all {cfg.v} names), time scaled linearly in rows')
+
+    # the other BASELINE.json configs on the same N GPUs
+    extra = {}
+    del rnd, host
+    torch.cuda.empty_cache()
+    if not args.no_extra:
+        try:
+            extra['c5'] = extra_block('C5', rank, world, group, peaks, args.extra_steps, 'rows')
+            extra['c4_vocab_shard'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'vocab')
+            extra['c4_rows'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'rows')
+            if world >= 4:
+                extra['c4_grid_2d'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'vocab', vocab_ways=2)
+        except Exception as e:
+            if world > 1:
+                raise                                              # a rank that skips a collective would hang the others
+            extra['error'] = str(e)[:300]
 
     if rank == 0:
         line = dict(metric=METRIC, value=round(ms_per_step, 4), unit='ms', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=round(ms_per_step, 4), higher_is_better=False, scaling='strong', vs_baseline=None, dtype='bf16',
-                    data='synthetic', config=config, clocks=clocks, e2e=e2e, gpu_launches=rnd.launches_per_round * args.steps,
+                    data='synthetic', config=config, clocks=clocks, e2e=e2e, gpu_launches=launches_per_round * args.steps,
                     launch_mode='cuda-graph replay' if graphed else 'eager',
-                    roofline=roofline, cpu_baseline=cpu_baseline,
-                    split=dict(naming_ms=round(name_ms, 4), rest_ms=round(ms_per_step - name_ms, 4)))
+                    roofline=roofline, cpu_baseline=cpu_baseline, torch_cuda_baseline=torch_base,
+                    split=dict(naming_ms=round(name_ms, 4), rest_ms=round(ms_per_step - name_ms, 4)),
+                    parity=parity, sustained=sustained, **extra)
         real_stdout.write(json.dumps(line) + '\n')
         real_stdout.flush()
     if world > 1:
         # Leave without tearing NCCL down: destroy_process_group() / interpreter exit can block for minutes while
         # a CUDA graph that captured NCCL kernels is still alive (seen on the 2-GPU box).  Every rank has passed
         # the final barrier and rank 0 has flushed its line, so a hard exit loses nothing.
-        rnd.graph = None
+        import torch.distributed as dist
+        dist.barrier(group=group)
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()

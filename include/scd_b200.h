@@ -51,25 +51,33 @@ SCD_API int scd_pairwise_distance(const float* X, int64_t N, int D, const float*
  * mindist = min_k dist, *inertia_acc += sum(mindist) (fp64 accumulator, caller zeroes it).
  * Tensor-core path (D % 8 == 0, D >= 40, K <= 1024, X 16-byte aligned): ||x||^2 - 2 x.c + ||c||^2 with the contraction
  * issued as three bf16 tcgen05 MMAs (hi/lo split of x and c, fp32 accumulate; X is read once, as fp32).
- * Other shapes: the fp32 direct-form kernel of scd_pairwise_distance with the argmin fused (exact = 1 forces it).
- * ws holds the per-iteration centroid hi/lo planes and norms. */
+ * Other shapes: the fp32 direct-form kernel of scd_pairwise_distance with the argmin fused (SCD_ESTEP_EXACT forces it).
+ * ws holds the per-iteration centroid hi/lo planes and norms; they are recomputed from C by a small kernel unless
+ * SCD_ESTEP_PLANES_READY says the previous scd_finalize_centers already left them there. */
+#define SCD_ESTEP_EXACT 1          /* force the fp32 direct-form kernel */
+#define SCD_ESTEP_PLANES_READY 2   /* ws already holds the operands of C: scd_finalize_centers(estep_ws = ws) wrote them */
 SCD_API size_t scd_estep_workspace_bytes(int K, int D);
+/* 1 when (N, D, K) takes the tensor-core path (given an aligned X and a workspace) - what the host layer needs to know
+ * before it asks scd_finalize_centers to prepare the next E-step's operands. */
+SCD_API int scd_estep_uses_tensor_cores(int64_t N, int D, int K);
 SCD_API int scd_estep(const float* X, int64_t N, int D, const float* C, int K,
-              int64_t* labels, float* mindist /* nullable */, double* inertia_acc /* nullable */, int exact,
+              int64_t* labels, float* mindist /* nullable */, double* inertia_acc /* nullable */, int flags,
               void* ws, size_t ws_bytes, scd_stream_t stream);
 
 /* k-means++ seeding, faster_mix_k_means_pytorch.py:20-36 (gcd copy :82-110), without the per-centre N x c distance
  * matrix and without a host round trip per centre:
  *   scd_kpp_update: d2[i] = min(d2[i], ||X_i - X[*pick]||^2) (first != 0: plain assignment), center_out[:] = X[*pick]
- *                   (nullable), per-block fp64 sums of d2 into ws; *pick < 0 leaves d2 as it is;
+ *                   (nullable), per-block fp64 sums of d2 into ws; *pick < 0 leaves d2 as it is; `center` (row-sharded
+ *                   seeding, SURVEY 8e: the picked row was broadcast by the rank that owns it) replaces X[*pick];
  *   scd_kpp_select: the reference's draw  prob = d2/sum(d2); ind = first i with cumsum(prob)[i] >= r  (:31-34) resolved
  *                   on the device with fp64 prefix sums; when no row qualifies *pick keeps its value and *no_hit |= 1
  *                   (|= 2 if *pick < 0, i.e. nothing to reuse; sticky, the caller zeroes it once): the gcd copy
  *                   :104-107 reuses the previous index, the local copy :34 raises IndexError.
  *                   sums_valid = 0 recomputes the block sums from d2 first (d2 produced by scd_estep's mindist). */
 SCD_API size_t scd_kpp_workspace_bytes(int64_t N);
-SCD_API int scd_kpp_update(const float* X, int64_t N, int D, const int64_t* pick, int first, float* d2,
-                   float* center_out /* nullable, [D] */, void* ws, size_t ws_bytes, scd_stream_t stream);
+SCD_API int scd_kpp_update(const float* X, int64_t N, int D, const int64_t* pick /* nullable when center */,
+                   const float* center /* nullable, [D]: measure against this vector instead of X[*pick] */, int first,
+                   float* d2, float* center_out /* nullable, [D] */, void* ws, size_t ws_bytes, scd_stream_t stream);
 SCD_API int scd_kpp_select(const float* d2, int64_t N, int sums_valid, double r, int64_t* pick, int32_t* no_hit,
                    void* ws, size_t ws_bytes, scd_stream_t stream);
 
@@ -85,17 +93,21 @@ SCD_API size_t scd_mstep_workspace_bytes(int64_t N, int K);
 SCD_API int scd_mstep_sums(const float* X, const int64_t* labels, int64_t N, int D, int K,
                    float* sums /* [K,D] */, int32_t* counts /* [K] */, void* ws, size_t ws_bytes, scd_stream_t stream);
 
-/* centers = sums / counts (empty cluster -> NaN row, like torch.mean over zero rows; no relocation), and
- * faster_mix_k_means_pytorch.py:71 / :123: *shift = sum_k ||C_new[k]-C_old[k]||_2 (C_old, shift nullable).
- * counts_f (nullable) takes float counts instead (e.g. after a packed fp32 all-reduce). ws: K floats. */
 /* Row-sharded k-means: tail of the packed fp32 all-reduce buffer [K*D sums | K counts | inertia]:
  * out[0..K) = (float)counts, out[K] = (float)*inertia (0 when NULL).  The host layer all-reduces the buffer
  * (NCCL) between scd_mstep_sums and scd_finalize_centers(counts_f = out). */
 SCD_API int scd_pack_counts_inertia(const int32_t* counts, const double* inertia /* nullable */, int K, float* out,
                             scd_stream_t stream);
 
+/* centers = sums / counts (empty cluster -> NaN row, like torch.mean over zero rows; no relocation), and
+ * faster_mix_k_means_pytorch.py:71 / :123: ws[k] = ||C_new[k]-C_old[k]||_2 (K floats, when C_old and ws are given) and
+ * *shift = sum_k ws[k] (nullable: the host layer reads the K norms with the inertia and adds them itself, which
+ * saves a launch).  counts_f (nullable) takes float counts instead (e.g. after a packed fp32 all-reduce).
+ * estep_ws (nullable, scd_estep_workspace_bytes(K, D)): also receives the next E-step's operands of C_new (bf16 hi / lo
+ * planes + ||c||^2, bit-identical to what scd_estep derives from C_new), see SCD_ESTEP_PLANES_READY. */
 SCD_API int scd_finalize_centers(const float* sums, const int32_t* counts, const float* counts_f, const float* C_old,
-                         float* C_new, float* shift, int K, int D, void* ws, size_t ws_bytes, scd_stream_t stream);
+                         float* C_new, float* shift, int K, int D, void* ws, size_t ws_bytes,
+                         void* estep_ws /* nullable */, size_t estep_ws_bytes, scd_stream_t stream);
 
 /* ---------------------------------------------------------------- naming (a8, a9, a11) */
 
@@ -133,13 +145,17 @@ SCD_API int scd_topk_merge(const float* part_vals, const int64_t* part_idx, cons
 /* main_unsup.py:575-582 / main_ptsup.py:636-644: per cluster c, Counter over topk_idx[cluster_of_row==c, :k_used]
  * minus `excluded` names, then most_common(M) with Python's tie order (first occurrence in the row-major
  * flattening).  out_names [K,M] int64 (-1 padded), out_counts [K,M], out_distinct [K] (#distinct names),
- * out_rows [K] (#rows in cluster).  *overflow (device int) set to 1 if a cluster had more distinct names
- * than the 16384-slot table. */
+ * out_rows [K] (#rows in cluster).
+ * A cluster's name histogram lives in a 16384-slot shared-memory table while rows * k_used <= 8192; larger clusters
+ * build it in `spill` (nullable; scd_vote_spill_bytes(N, k_used) bytes of device memory, 24 bytes per top-k entry).
+ * Without a spill buffer such a cluster can exhaust the table: *overflow (device int) is then set to 1 and its counts
+ * are incomplete - callers must check it. */
 SCD_API size_t scd_vote_workspace_bytes(int64_t N, int K);
+SCD_API size_t scd_vote_spill_bytes(int64_t N, int k_used);
 SCD_API int scd_vote(const int64_t* topk_idx, int k_total, int k_used, const int64_t* cluster_of_row, int64_t N, int K,
              const int64_t* excluded, int n_excluded, int M, int64_t* out_names, int32_t* out_counts,
              int32_t* out_distinct, int32_t* out_rows, int32_t* overflow, void* ws, size_t ws_bytes,
-             scd_stream_t stream);
+             void* spill /* nullable */, size_t spill_bytes, scd_stream_t stream);
 
 /* Same vote when the rows were already sorted by these very cluster labels: `mstep_ws` is the workspace a
  * scd_mstep_sums(X, labels, N, D, K, ...) call on the same labels has just filled (k-means labels are what
@@ -148,7 +164,17 @@ SCD_API int scd_vote(const int64_t* topk_idx, int k_total, int k_used, const int
 SCD_API int scd_vote_presorted(const int64_t* topk_idx, int k_total, int k_used, const void* mstep_ws, int64_t N, int K,
                        const int64_t* excluded /* nullable */, int n_excluded, int M,
                        int64_t* out_names, int32_t* out_counts, int32_t* out_distinct, int32_t* overflow,
-                       scd_stream_t stream);
+                       void* spill /* nullable */, size_t spill_bytes, scd_stream_t stream);
+
+/* Row-sharded multi-GPU vote: rec[i] = [label_i, name_i0 .. name_i(k_used-1)] as int32 - one record per
+ * image row, so ONE all-gather moves a rank's labels and top-k names (4 * (1 + k_used) bytes per row) and
+ * scd_vote_records runs the vote of main_unsup.py:575-582 on the gathered records (same outputs as scd_vote). */
+SCD_API int scd_pack_vote_records(const int64_t* labels, const int64_t* topk_idx, int k_total, int k_used, int64_t n,
+                          int32_t* rec /* [n, 1 + k_used] */, scd_stream_t stream);
+SCD_API int scd_vote_records(const int32_t* rec, int k_used, int64_t N, int K, const int64_t* excluded /* nullable */,
+                     int n_excluded, int M, int64_t* out_names, int32_t* out_counts, int32_t* out_distinct,
+                     int32_t* out_rows, int32_t* overflow, void* ws, size_t ws_bytes,
+                     void* spill /* nullable */, size_t spill_bytes, scd_stream_t stream);
 
 /* ---------------------------------------------------------------- size-constrained assignment (a7) */
 

@@ -20,15 +20,16 @@ SIGNATURES = {
     'scd_debug_set_name_profile': (None, [_vp]),
     'scd_pairwise_distance': (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp]),
     'scd_estep_workspace_bytes': (_sz, [_int, _int]),
+    'scd_estep_uses_tensor_cores': (_int, [_i64, _int, _int]),
     'scd_estep': (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
     'scd_kpp_workspace_bytes': (_sz, [_i64]),
-    'scd_kpp_update': (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _sz, _vp]),
+    'scd_kpp_update': (_int, [_vp, _i64, _int, _vp, _vp, _int, _vp, _vp, _vp, _sz, _vp]),
     'scd_kpp_select': (_int, [_vp, _i64, _int, C.c_double, _vp, _vp, _vp, _sz, _vp]),
     'scd_labelled_inertia': (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp, _vp]),
     'scd_mstep_workspace_bytes': (_sz, [_i64, _int]),
     'scd_mstep_sums': (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _sz, _vp]),
     'scd_pack_counts_inertia': (_int, [_vp, _vp, _int, _vp, _vp]),
-    'scd_finalize_centers': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _vp]),
+    'scd_finalize_centers': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _vp, _sz, _vp]),
     'scd_vocab_prepare': (_int, [_vp, _int, _int, _i64, _i64, _vp, _vp]),
     'scd_cast_bf16': (_int, [_vp, _i64, _vp, _vp]),
     'scd_gather_rows_bf16': (_int, [_vp, _vp, _int, _int, _i64, _vp, _vp]),
@@ -37,13 +38,18 @@ SIGNATURES = {
     'scd_name_topk': (_int, [_vp, _i64, _int, _vp, _i64, _f32, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'scd_topk_merge': (_int, [_vp, _vp, _vp, _vp, _int, _i64, _int, _f32, _int, _vp, _vp, _vp]),
     'scd_vote_workspace_bytes': (_sz, [_i64, _int]),
-    'scd_vote': (_int, [_vp, _int, _int, _vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    'scd_vote_presorted': (_int, [_vp, _int, _int, _vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp]),
+    'scd_vote_spill_bytes': (_sz, [_i64, _int]),
+    'scd_vote': (_int, [_vp, _int, _int, _vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+    'scd_vote_presorted': (_int, [_vp, _int, _int, _vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'scd_pack_vote_records': (_int, [_vp, _vp, _int, _int, _i64, _vp, _vp]),
+    'scd_vote_records': (_int, [_vp, _int, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     'scd_label_histogram': (_int, [_vp, _i64, _int, _vp, _vp]),
     'scd_constrained_assign': (_int, [_vp, _i64, _int, _i64, _i64, _vp, C.POINTER(_i64), C.POINTER(_i64)]),
     'scd_contingency': (_int, [_vp, _int, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     'scd_linear_assignment': (_int, [_vp, _int, _int, _vp, C.POINTER(_int)]),
 }
+
+ESTEP_EXACT, ESTEP_PLANES_READY = 1, 2          # scd_estep flags (include/scd_b200.h)
 
 _lib = None
 

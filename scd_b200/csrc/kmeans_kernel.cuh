@@ -10,6 +10,7 @@
 // NCCL all-reduce can sit between when rows are sharded across GPUs).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <math.h>
 
@@ -118,7 +119,13 @@ sqdist_kernel(const float* __restrict__ X, long long N, int D, const float* __re
           const int gc = col0 + tc * 4 + j;
           if (gc < K) {
             if (out) out[gr * K + gc] = acc[i][j];
-            if (cost_x1000) cost_x1000[gr * K + gc] = (int)rintf(sqrtf(acc[i][j]) * 1000.f);
+            if (cost_x1000) {
+              // sskm_constrained.py:324: np.around(costs * 1000).astype(int32) on the float64 promotion of the fp32
+              // sqrt - the product is rounded in fp64 (an fp32 product can cross a .5 boundary); NaN (distance to an
+              // empty cluster's NaN centroid) becomes INT_MIN like NumPy's cast on x86
+              const float r = sqrtf(acc[i][j]);
+              cost_x1000[gr * K + gc] = r != r ? (int)0x80000000 : __double2int_rn((double)r * 1000.0);
+            }
           }
         }
       }
@@ -164,9 +171,20 @@ sqdist_kernel(const float* __restrict__ X, long long N, int D, const float* __re
 }
 
 // --------------------------------------------------------------------------------------------
-// M-step, part 1: counting sort of row ids by label (histogram -> exclusive scan -> scatter).
-// Labels outside [0, K) (e.g. the reference's -1 "unassigned") are ignored.
+// M-step, part 1: counting sort of row ids by label, two launches.
+//   label_hist_scan_kernel  per-block shared-memory histogram -> global accumulator; the LAST block to finish (ticket)
+//                           turns the accumulated counts into counts_out / offsets / cursor (exclusive scan) and
+//                           leaves accumulator and ticket zeroed for the next call.  Also zeroes `zero_me` (the
+//                           [K, D] sums the segment sum accumulates into) so no separate memset node is needed.
+//   label_scatter_kernel    a block ranks its 1024 rows per label in shared memory and reserves ONE range per
+//                           (block, label) in the global cursor: N / 1024 * min(K, 1024) global atomics instead of N
+//                           (round 1: 29 us for 127 k rows on 100 cursors, the contended L2 atomics serialise).
+// Labels are read through (pointer, element stride): int64 label vectors (stride 1) or the label column of the
+// packed int32 vote records [N][1 + k] of the multi-GPU path.  Labels outside [0, K) (e.g. the reference's -1
+// "unassigned") are ignored.  The order of the rows inside a cluster is not deterministic (atomics); the vote does
+// not depend on it (first positions are row ids), the fp32 segment sums do in their last bits.
 // --------------------------------------------------------------------------------------------
+// plain label histogram (scd_label_histogram: the size check of the constrained E-step)
 __global__ void label_hist_kernel(const long long* __restrict__ labels, long long N, int K, int* __restrict__ counts) {
   extern __shared__ int sh_hist[];
   for (int k = threadIdx.x; k < K; k += blockDim.x) sh_hist[k] = 0;
@@ -179,38 +197,85 @@ __global__ void label_hist_kernel(const long long* __restrict__ labels, long lon
   for (int k = threadIdx.x; k < K; k += blockDim.x) if (sh_hist[k]) atomicAdd(&counts[k], sh_hist[k]);
 }
 
-// single block: offsets[k] = sum_{j<k} counts[j]; offsets[K] = total; cursor[k] = offsets[k]
-__global__ void label_scan_kernel(const int* __restrict__ counts, int K, int* __restrict__ offsets, int* __restrict__ cursor) {
-  __shared__ int sh[1024];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
+constexpr int kSortThreads = 256;
+constexpr int kScatterRowsPerThread = 4;
+constexpr int kScatterRows = kSortThreads * kScatterRowsPerThread;      // rows per block of the scatter
+
+template <typename LabT>
+__global__ void __launch_bounds__(kSortThreads)
+label_hist_scan_kernel(const LabT* __restrict__ labels, long long stride, long long N, int K, int* __restrict__ acc /* [K] zero on entry */,
+                       unsigned* __restrict__ ticket /* zero on entry */, int* __restrict__ counts_out /* nullable */,
+                       int* __restrict__ offsets, int* __restrict__ cursor, float4* __restrict__ zero_me, long long n_zero4) {
+  extern __shared__ int sh_hist[];
+  __shared__ bool is_last;
+  __shared__ int sh_part[kSortThreads];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) sh_hist[k] = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_zero4; i += (long long)gridDim.x * blockDim.x)
+    zero_me[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  for (int base = 0; base < K; base += 1024) {
-    const int k = base + threadIdx.x;
-    const int v = k < K ? counts[k] : 0;
-    sh[threadIdx.x] = v;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    const long long l = (long long)labels[i * stride];
+    if (l >= 0 && l < K) atomicAdd(&sh_hist[(int)l], 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) if (sh_hist[k]) atomicAdd(&acc[k], sh_hist[k]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // exclusive scan over K counts: thread t owns the contiguous slice [t * per, (t + 1) * per)
+  const int per = (K + kSortThreads - 1) / kSortThreads;
+  const int k0 = min(threadIdx.x * per, K), k1 = min(k0 + per, K);
+  int local = 0;
+  for (int k = k0; k < k1; ++k) local += __ldcg(&acc[k]);
+  sh_part[threadIdx.x] = local;
+  __syncthreads();
+  for (int off = 1; off < kSortThreads; off <<= 1) {
+    const int t = (int)threadIdx.x >= off ? sh_part[threadIdx.x - off] : 0;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-      const int t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
-    }
-    const int excl = carry + sh[threadIdx.x] - v;
-    if (k < K) { offsets[k] = excl; cursor[k] = excl; }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += sh[1023];
+    sh_part[threadIdx.x] += t;
     __syncthreads();
   }
-  if (threadIdx.x == 0) offsets[K] = carry;
+  int run = sh_part[threadIdx.x] - local;
+  for (int k = k0; k < k1; ++k) {
+    const int c = __ldcg(&acc[k]);
+    offsets[k] = run; cursor[k] = run;
+    if (counts_out) counts_out[k] = c;
+    acc[k] = 0;
+    run += c;
+  }
+  if (threadIdx.x == kSortThreads - 1) { offsets[K] = sh_part[kSortThreads - 1]; *ticket = 0u; }
 }
 
-__global__ void label_scatter_kernel(const long long* __restrict__ labels, long long N, int K, int* __restrict__ cursor,
-                                     int* __restrict__ order) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-    const long long l = labels[i];
-    if (l >= 0 && l < K) order[atomicAdd(&cursor[(int)l], 1)] = (int)i;
+template <typename LabT>
+__global__ void __launch_bounds__(kSortThreads)
+label_scatter_kernel(const LabT* __restrict__ labels, long long stride, long long N, int K, int* __restrict__ cursor,
+                     int* __restrict__ order) {
+  extern __shared__ int sh_cnt[];          // [K] rows of this block per label, then the block's base per label
+  for (int k = threadIdx.x; k < K; k += blockDim.x) sh_cnt[k] = 0;
+  __syncthreads();
+  const long long row0 = (long long)blockIdx.x * kScatterRows;
+  int lab[kScatterRowsPerThread], rank[kScatterRowsPerThread];
+#pragma unroll
+  for (int q = 0; q < kScatterRowsPerThread; ++q) {
+    const long long i = row0 + q * kSortThreads + threadIdx.x;
+    lab[q] = -1;
+    if (i < N) {
+      const long long l = (long long)labels[i * stride];
+      if (l >= 0 && l < K) { lab[q] = (int)l; rank[q] = atomicAdd(&sh_cnt[(int)l], 1); }
+    }
   }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const int c = sh_cnt[k];
+    if (c) sh_cnt[k] = atomicAdd(&cursor[k], c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < kScatterRowsPerThread; ++q)
+    if (lab[q] >= 0) order[sh_cnt[lab[q]] + rank[q]] = (int)(row0 + q * kSortThreads + threadIdx.x);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -291,26 +356,39 @@ __global__ void segment_sum_generic_kernel(const float* __restrict__ X, const in
   sums[(long long)k * D + d] = acc;
 }
 
-// centers = sums / counts (0/0 -> NaN, as torch's mean over zero rows), per-cluster move norm
+// centers = sums / counts (0/0 -> NaN, as torch's mean over zero rows), per-cluster move norm; optionally also the
+// next E-step's operands of the new centres - bf16 hi / lo planes and ||c||^2, exactly what centroid_split_kernel
+// (estep_tc_kernel.cuh) would compute from c_new, same summation order - so the iteration loop needs no split launch.
 __global__ void finalize_centers_kernel(const float* __restrict__ sums, const float* __restrict__ counts_f, const int* __restrict__ counts_i,
                                         const float* __restrict__ c_old, float* __restrict__ c_new, float* __restrict__ move_norm,
-                                        int K, int D) {
+                                        int K, int D, __nv_bfloat16* __restrict__ plane_hi, __nv_bfloat16* __restrict__ plane_lo,
+                                        float* __restrict__ cnorm) {
   const int k = blockIdx.x;
   const float cnt = counts_i ? (float)counts_i[k] : counts_f[k];
-  float part = 0.f;
+  float part = 0.f, npart = 0.f;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     const float c = sums[(long long)k * D + d] / cnt;
     c_new[(long long)k * D + d] = c;
     if (c_old) { const float df = c - c_old[(long long)k * D + d]; part += df * df; }
+    if (plane_hi) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(c);
+      plane_hi[(long long)k * D + d] = h;
+      plane_lo[(long long)k * D + d] = __float2bfloat16_rn(c - __bfloat162float(h));
+      npart = fmaf(c, c, npart);
+    }
   }
-  __shared__ float sh[32];
-  for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+  __shared__ float sh[32], shn[32];
+  for (int off = 16; off > 0; off >>= 1) {
+    part += __shfl_down_sync(0xffffffffu, part, off);
+    npart += __shfl_down_sync(0xffffffffu, npart, off);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = part; shn[threadIdx.x >> 5] = npart; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += sh[w];
+    float t = 0.f, tn = 0.f;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) { t += sh[w]; tn += shn[w]; }
     if (move_norm) move_norm[k] = sqrtf(t);
+    if (cnorm) cnorm[k] = tn;
   }
 }
 
@@ -371,14 +449,15 @@ gather_sqdist_kernel(const float* __restrict__ L, const long long* __restrict__ 
 // --------------------------------------------------------------------------------------------
 constexpr int kKppRowsPerBlock = 64;     // 8 warps x 8 rows
 
-// d2[i] = min(d2[i], ||X_i - X[*pick]||^2)  (first == 1: no min, plain assignment);  also centers_out[:] = X[*pick].
+// d2[i] = min(d2[i], ||X_i - c||^2) with c = `center` when given (row-sharded seeding: the picked row lives on another
+// rank and arrives by broadcast), else X[*pick]  (first == 1: no min, plain assignment);  also centers_out[:] = c.
 // *pick < 0 (no candidate was found by the select step) leaves d2 untouched and only refreshes the block sums.
 __global__ void __launch_bounds__(256)
-kpp_update_kernel(const float* __restrict__ X, long long N, int D, const long long* __restrict__ pick, int first,
-                  float* __restrict__ d2, double* __restrict__ block_sums, float* __restrict__ center_out) {
-  const long long src = *pick;
+kpp_update_kernel(const float* __restrict__ X, long long N, int D, const long long* __restrict__ pick, const float* __restrict__ center,
+                  int first, float* __restrict__ d2, double* __restrict__ block_sums, float* __restrict__ center_out) {
+  const long long src = center ? 0 : *pick;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* c = X + (src >= 0 ? src : 0) * D;
+  const float* c = center ? center : X + (src >= 0 ? src : 0) * D;
   if (blockIdx.x == 0 && center_out && src >= 0)
     for (int d = threadIdx.x; d < D; d += blockDim.x) center_out[d] = c[d];
   double local = 0.0;

@@ -103,6 +103,7 @@ struct NameParams {
   long long* prof;         // nullable: [pairs][16] cycle counters (scd_debug_set_name_profile), debugging aid
   const __nv_bfloat16* x;  // [N, d] row-major: the loader warps read the TMEM-resident k-blocks straight from global memory
   int d;
+  unsigned wait_hint_ns;   // 0: plain try_wait spin; > 0: suspend-time hint of the long waits (producers, loaders, epilogue)
 };
 
 // One sorted top-KT list in registers, ordered by (value descending, column ascending) - the order
@@ -255,7 +256,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           const int stage = (int)(g % kBStages);
           const uint32_t phase = (g / kBStages) & 1u;
           { const long long c0 = prof ? clock64() : 0;
-            ptx::mbar_wait(empty_bar(stage), phase ^ 1, 200 + stage);
+            ptx::mbar_wait_hint(empty_bar(stage), phase ^ 1, 200 + stage, p.wait_hint_ns);
             if (prof) pf_e += clock64() - c0; }
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * kBStageBytes);
@@ -289,7 +290,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           if (row < p.n_rows && kb * kAKBlock + q * 8 < p.d) v = __ldg(src + kb * 8 + q);
           r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
         }
-        ptx::mbar_wait(a_empty_bar(kb), (my_item_no & 1) ^ 1, 150 + kb);
+        ptx::mbar_wait_hint(a_empty_bar(kb), (my_item_no & 1) ^ 1, 150 + kb, p.wait_hint_ns);
         ptx::tc_fence_after_sync();
         ptx::tmem_st_32x32(tmem_base + lane_addr + a_tmem_col(kb, 0), r);
         ptx::tmem_st_wait();
@@ -302,7 +303,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       if (warp == 12) {
         const int row0 = item_rb(it) * 2 * kBlockM + (int)cta_rank * kBlockM;
         for (int kb = kTmemAKBlocks; kb < nkb; ++kb) {
-          ptx::mbar_wait(a_empty_bar(kb), (my_item_no & 1) ^ 1, 100 + kb);
+          ptx::mbar_wait_hint(a_empty_bar(kb), (my_item_no & 1) ^ 1, 100 + kb, p.wait_hint_ns);
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_arrive_expect_tx(a_full_bar(kb), 2 * kABlockBytes);
             ptx::tma_load_2d<2>(sbase + NameSmem::a_off + (kb - kTmemAKBlocks) * kABlockBytes, &map_x,
@@ -471,7 +472,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         const int half_cols = half == 0 ? kHalfCols : kTileN - kHalfCols;
         const int n_valid = (int)min((long long)half_cols, p.v_total - col0);      // may be <= 0 on the last tile
         { const long long c0 = prof ? clock64() : 0;
-          ptx::mbar_wait(tmem_full_bar(buf), (tile_no >> 1) & 1u, 600 + buf);
+          ptx::mbar_wait_hint(tmem_full_bar(buf), (tile_no >> 1) & 1u, 600 + buf, p.wait_hint_ns);
           if (prof) pf_w += clock64() - c0; }
         ptx::tc_fence_after_sync();
         const long long tr0 = trace ? clock64() : 0;
@@ -500,46 +501,82 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         if (trace && lane == 0 && n_ev < 128) { trace[3 * n_ev] = tr0; trace[3 * n_ev + 1] = tr1; trace[3 * n_ev + 2] = clock64(); ++n_ev; }
       }
 
-      // Exact top-k of the row from its (at most KT) parked chunks, in two divergence-free passes (a naive
-      // "push every element" scan costs ~17k warp-instructions because the 32 rows of a warp accept at
-      // different positions; it stalled the tensor pipe for ~90k cycles per work item):
-      //  1. every parked chunk contributes its own maximum, so the k-th best element is at least the
-      //     smallest parked maximum; elements below it are dropped, survivors (typically 5-10 of 160) are
-      //     appended to a per-thread candidate list in local memory with predicated stores;
-      //  2. the warp walks the candidate lists in lock step (trip count = longest list in the warp).
+      // Exact top-k of the row from its (at most KT) parked chunks.  Every parked chunk contributes its own maximum, so
+      // the k-th best element is at least T = the smallest parked maximum; only elements >= T can be in the top-k
+      // and on real score distributions there are k .. k + 3 of them among the KT * 32 parked values.
+      //  1. one pass over the parked chunks (next chunk's loads in flight behind the current one's compares) builds a
+      //     32-bit survivor mask per chunk - no value is kept, no local memory is touched;
+      //  2. the first survivor of every chunk is re-read from the scratch slot (KT independent loads in flight) and
+      //     pushed, then a short lock-step loop drains the few remaining bits.
+      // ~1 k warp-instructions and ~2-3 k cycles per work item, which hides behind the two tiles the issuers can run
+      // ahead into the double-buffered accumulators.  (Round 1 appended survivors to per-thread candidate lists in
+      // local memory: divergent st.local, ~28 k cycles per item with the tensor pipe idle for ~18 k of them - 4 % of a
+      // whole-vocabulary sweep but 20-37 % of the short items a small row shard is cut into)
       const long long pf_c1 = prof ? clock64() : 0;
       TopK<KT> top;
       top.reset();
       {
-        float cand_v[KT * 32];
-        int cand_i[KT * 32];
-        int nc = 0;
         const float keep_from = ctop.m[KT - 1];
-#pragma unroll
-        for (int e = 0; e < KT; ++e) {
-          const int col_e = ctop.col[e];
+        uint32_t mask[KT];
+        float4 xa[8], xb[8];
+        auto load_chunk = [&](int e, float4 (&x)[8]) {
           const float4* src = my_scratch + ctop.slot[e] * 8;
-          float4 x[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) x[q] = col_e >= 0 ? src[q] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          for (int q = 0; q < 8; ++q) x[q] = ctop.col[e] >= 0 ? src[q] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        };
+        auto survivors = [&](const float4 (&x)[8]) {
+          uint32_t m = 0u;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float xv[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              if (col_e >= 0 && xv[w] >= keep_from && xv[w] > -INFINITY) { cand_v[nc] = xv[w]; cand_i[nc] = col_e + 4 * q + w; ++nc; }
-            }
+            for (int w = 0; w < 4; ++w)
+              if (xv[w] >= keep_from && xv[w] > -INFINITY) m |= 1u << (4 * q + w);
           }
-        }
-        int nmax = nc;
+          return m;
+        };
+        load_chunk(0, xa);
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, off));
+        for (int e = 0; e < KT; ++e) {
+          if (e + 1 < KT) { if (e & 1) load_chunk(e + 1, xa); else load_chunk(e + 1, xb); }
+          mask[e] = (e & 1) ? survivors(xb) : survivors(xa);
+        }
+        // first survivor of every chunk: KT independent scalar re-reads in flight, then KT pushes
+        float v0[KT];
+        int c0[KT];
+#pragma unroll
+        for (int e = 0; e < KT; ++e) {
+          const bool live = mask[e] != 0u;
+          const int j = live ? __ffs((int)mask[e]) - 1 : 0;
+          const float* src = reinterpret_cast<const float*>(my_scratch + ctop.slot[e] * 8);
+          v0[e] = live ? src[j] : -INFINITY;
+          c0[e] = live ? ctop.col[e] + j : -1;
+          mask[e] &= mask[e] - 1u;                    // 0 stays 0
+        }
+#pragma unroll
+        for (int e = 0; e < KT; ++e) top.push(v0[e], c0[e]);
+        // the rest (usually nothing, or one or two bits in a warp): lock-step, lowest chunk first
+        uint32_t left = 0u;
+#pragma unroll
+        for (int e = 0; e < KT; ++e) left |= mask[e];
 #pragma unroll 1
-        for (int c = 0; c < nmax; ++c) {
-          const bool live = c < nc;
-          const float v = live ? cand_v[c] : -INFINITY;
-          const int ix = live ? cand_i[c] : -1;
-          top.push(v, ix);
+        while (__any_sync(0xffffffffu, left != 0u)) {
+          uint32_t m = 0u;
+          int slot_sel = 0, col_sel = 0;
+#pragma unroll
+          for (int e = KT - 1; e >= 0; --e)
+            if (mask[e] != 0u) { m = mask[e]; slot_sel = ctop.slot[e]; col_sel = ctop.col[e]; }
+          const bool live = m != 0u;
+          const int j = live ? __ffs((int)m) - 1 : 0;
+          const float v = live ? reinterpret_cast<const float*>(my_scratch + slot_sel * 8)[j] : -INFINITY;
+          top.push(v, live ? col_sel + j : -1);
+          bool cleared = false;
+          left = 0u;
+#pragma unroll
+          for (int e = 0; e < KT; ++e) {
+            if (!cleared && mask[e] != 0u) { mask[e] &= mask[e] - 1u; cleared = true; }
+            left |= mask[e];
+          }
         }
       }
       if (row < p.n_rows) {

@@ -173,6 +173,16 @@ bool plan_naming(int64_t N, int64_t V, int k, NamePlan* pl) {
   return true;
 }
 
+// suspend-time hint (ns) of the naming kernel's long mbarrier waits; SCD_NAME_WAIT_HINT_NS overrides (0 = plain spin)
+unsigned name_wait_hint_ns() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = std::getenv("SCD_NAME_WAIT_HINT_NS");
+    cached = e ? std::max(0, std::atoi(e)) : 0;
+  }
+  return (unsigned)cached;
+}
+
 template <int KT>
 int launch_name_topk(const CUtensorMap& mx, const CUtensorMap& mw, const scd::NameParams& p, int n_pairs, cudaStream_t st) {
   static bool attr_set[kMaxDevices] = {};
@@ -187,11 +197,63 @@ int launch_name_topk(const CUtensorMap& mx, const CUtensorMap& mw, const scd::Na
   return 0;
 }
 
+// ---- counting sort of rows by label: workspace carving shared by the M-step and the vote
+// ints: offsets[K+1] | cursor[K] | acc[K] | ticket[1] | order[N]
+struct SortWs {
+  int* offsets; int* cursor; int* acc; unsigned* ticket; int* order;
+  SortWs(void* ws, int K) {
+    offsets = reinterpret_cast<int*>(ws);
+    cursor = offsets + K + 1;
+    acc = cursor + K;
+    ticket = reinterpret_cast<unsigned*>(acc + K);
+    order = acc + K + 1;
+  }
+  static size_t ints(int64_t N, int K) { return 3 * (size_t)K + 2 + (size_t)std::max<int64_t>(N, 0); }
+};
+constexpr int kMaxSortK = 11264;          // 44 KB of shared-memory counters (+ the static scan scratch stays under 48 KB)
+
+template <typename LabT>
+int sort_rows_by_label(const LabT* labels, long long stride, int64_t N, int K, int32_t* counts_out, const SortWs& w,
+                              float* zero_me, size_t n_zero_floats, cudaStream_t st) {
+  SCD_CUDA(cudaMemsetAsync(w.acc, 0, sizeof(int) * ((size_t)K + 1), st));          // accumulator + ticket
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((N + scd::kSortThreads - 1) / scd::kSortThreads, 148 * 4));
+  scd::label_hist_scan_kernel<LabT><<<blocks, scd::kSortThreads, sizeof(int) * (size_t)K, st>>>(
+      labels, stride, N, K, w.acc, w.ticket, counts_out, w.offsets, w.cursor, reinterpret_cast<float4*>(zero_me),
+      (long long)(n_zero_floats / 4));
+  SCD_LAUNCH_CHECK("label_hist_scan_kernel");
+  if (N > 0) {
+    const int sblocks = (int)((N + scd::kScatterRows - 1) / scd::kScatterRows);
+    scd::label_scatter_kernel<LabT><<<sblocks, scd::kSortThreads, sizeof(int) * (size_t)K, st>>>(labels, stride, N, K, w.cursor, w.order);
+    SCD_LAUNCH_CHECK("label_scatter_kernel");
+  }
+  return 0;
+}
+
+template <typename IdxT>
+int launch_vote(const IdxT* topk_idx, long long idx_stride, int k_used, int64_t N, const int* order, const int* offsets, int K,
+                       const int64_t* excluded, int n_excluded, int M, int64_t* out_names, int32_t* out_counts,
+                       int32_t* out_distinct, int32_t* overflow, void* spill, size_t spill_bytes, cudaStream_t st) {
+  if (spill && spill_bytes < scd::vote_spill_bytes(N, k_used)) return fail("vote: spill buffer too small (%zu < %zu)", spill_bytes, scd::vote_spill_bytes(N, k_used));
+  SCD_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), st));
+  static bool attr_set[kMaxDevices][2] = {};
+  const int dev = current_device_slot();
+  constexpr int which = sizeof(IdxT) == 8 ? 0 : 1;
+  if (!attr_set[dev][which]) {
+    SCD_CUDA(cudaFuncSetAttribute(scd::vote_kernel<IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, scd::kVoteSmemBytes));
+    attr_set[dev][which] = true;
+  }
+  scd::vote_kernel<IdxT><<<K, scd::kVoteThreads, scd::kVoteSmemBytes, st>>>(
+      topk_idx, idx_stride, k_used, order, offsets, K, reinterpret_cast<const long long*>(excluded), n_excluded, M,
+      reinterpret_cast<long long*>(out_names), out_counts, out_distinct, overflow, reinterpret_cast<int*>(spill));
+  SCD_LAUNCH_CHECK("vote_kernel");
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
 
-int scd_version(void) { return 100; }
+int scd_version(void) { return 200; }
 
 void scd_debug_set_name_profile(void* dev_buf_pairs_x16_i64) { g_name_prof = reinterpret_cast<long long*>(dev_buf_pairs_x16_i64); }
 
@@ -209,21 +271,26 @@ int scd_pairwise_distance(const float* X, int64_t N, int D, const float* C, int 
   return 0;
 }
 
+int scd_estep_uses_tensor_cores(int64_t N, int D, int K) {
+  return D % 8 == 0 && D > scd::kEsBK * (scd::kEsConvSets - 1) && K > 0 && K <= scd::kEsMaxK && N < (1ll << 31) ? 1 : 0;
+}
+
 size_t scd_estep_workspace_bytes(int K, int D) {
   if (K <= 0 || D <= 0) return 256;
   return align_up((size_t)K * D * 2, 256) * 2 + align_up((size_t)K * sizeof(float), 256) + 256;
 }
 
 int scd_estep(const float* X, int64_t N, int D, const float* C, int K, int64_t* labels, float* mindist, double* inertia_acc,
-              int exact, void* ws, size_t ws_bytes, scd_stream_t stream) {
+              int flags, void* ws, size_t ws_bytes, scd_stream_t stream) {
   if (N < 0 || D <= 0 || K <= 0) return fail("scd_estep: bad shape N=%lld D=%d K=%d", (long long)N, D, K);
   if (N == 0) return 0;
   if (!X || !C || !labels) return fail("scd_estep: null pointer");
+  const bool exact = (flags & SCD_ESTEP_EXACT) != 0;
   cudaStream_t st = as_stream(stream);
   // TMA needs 16-byte row pitches: fp32 X (D % 4) and the bf16 centroid planes (D % 8); every converter
   // warp set must own at least one k-block per tile (it publishes its share of ||x||^2 there)
-  const bool tc_ok = !exact && D % 8 == 0 && D > scd::kEsBK * (scd::kEsConvSets - 1) && K <= scd::kEsMaxK && N < (1ll << 31) &&
-                     (reinterpret_cast<uintptr_t>(X) & 15) == 0 && ws && ws_bytes >= scd_estep_workspace_bytes(K, D);
+  const bool tc_ok = !exact && scd_estep_uses_tensor_cores(N, D, K) && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && ws &&
+                     ws_bytes >= scd_estep_workspace_bytes(K, D);
   if (!tc_ok) {
     dim3 grid((unsigned)((N + scd::kDistBM - 1) / scd::kDistBM));
     scd::sqdist_kernel<true><<<grid, scd::kDistThreads, 0, st>>>(X, N, D, C, K, nullptr, nullptr,
@@ -236,8 +303,10 @@ int scd_estep(const float* X, int64_t N, int D, const float* C, int K, int64_t* 
   __nv_bfloat16* chi = reinterpret_cast<__nv_bfloat16*>(w8);
   __nv_bfloat16* clo = reinterpret_cast<__nv_bfloat16*>(w8 + plane);
   float* cnorm = reinterpret_cast<float*>(w8 + 2 * plane);
-  scd::centroid_split_kernel<<<K, 256, 0, st>>>(C, K, D, chi, clo, cnorm);
-  SCD_LAUNCH_CHECK("centroid_split_kernel");
+  if (!(flags & SCD_ESTEP_PLANES_READY)) {      // scd_finalize_centers(estep_ws = ws) already left the planes of C there
+    scd::centroid_split_kernel<<<K, 256, 0, st>>>(C, K, D, chi, clo, cnorm);
+    SCD_LAUNCH_CHECK("centroid_split_kernel");
+  }
 
   scd::EsParams p;
   p.n_rows = N;
@@ -294,13 +363,13 @@ size_t scd_kpp_workspace_bytes(int64_t N) {
   return align_up(nb * sizeof(double), 256) + 256;
 }
 
-int scd_kpp_update(const float* X, int64_t N, int D, const int64_t* pick, int first, float* d2, float* center_out, void* ws,
-                   size_t ws_bytes, scd_stream_t stream) {
+int scd_kpp_update(const float* X, int64_t N, int D, const int64_t* pick, const float* center, int first, float* d2,
+                   float* center_out, void* ws, size_t ws_bytes, scd_stream_t stream) {
   if (N <= 0 || D <= 0) return fail("scd_kpp_update: bad shape N=%lld D=%d", (long long)N, D);
-  if (!X || !pick || !d2 || !ws) return fail("scd_kpp_update: null pointer");
+  if (!X || (!pick && !center) || !d2 || !ws) return fail("scd_kpp_update: null pointer");
   if (ws_bytes < scd_kpp_workspace_bytes(N)) return fail("scd_kpp_update: workspace too small");
   const int nb = (int)((N + scd::kKppRowsPerBlock - 1) / scd::kKppRowsPerBlock);
-  scd::kpp_update_kernel<<<nb, 256, 0, as_stream(stream)>>>(X, N, D, reinterpret_cast<const long long*>(pick), first, d2,
+  scd::kpp_update_kernel<<<nb, 256, 0, as_stream(stream)>>>(X, N, D, reinterpret_cast<const long long*>(pick), center, first, d2,
                                                             reinterpret_cast<double*>(ws), center_out);
   SCD_LAUNCH_CHECK("kpp_update_kernel");
   return 0;
@@ -334,31 +403,11 @@ int scd_labelled_inertia(const float* L, const int64_t* labels, int64_t n, int D
   return 0;
 }
 
-// workspace layout (ints): offsets[K+1] | cursor[K] | order[N]
-size_t scd_mstep_workspace_bytes(int64_t N, int K) {
-  return align_up((size_t)(2 * (size_t)K + 1 + (size_t)std::max<int64_t>(N, 0)) * sizeof(int), 256) + 256;
-}
-
-static int sort_rows_by_label(const int64_t* labels, int64_t N, int K, int32_t* counts, int* offsets, int* cursor, int* order,
-                              cudaStream_t st) {
-  SCD_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)K, st));
-  const int blocks = (int)std::min<long long>((N + 255) / 256, 148 * 8);
-  if (N > 0) {
-    scd::label_hist_kernel<<<blocks, 256, sizeof(int) * (size_t)K, st>>>(reinterpret_cast<const long long*>(labels), N, K, counts);
-    SCD_LAUNCH_CHECK("label_hist_kernel");
-  }
-  scd::label_scan_kernel<<<1, 1024, 0, st>>>(counts, K, offsets, cursor);
-  SCD_LAUNCH_CHECK("label_scan_kernel");
-  if (N > 0) {
-    scd::label_scatter_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(labels), N, K, cursor, order);
-    SCD_LAUNCH_CHECK("label_scatter_kernel");
-  }
-  return 0;
-}
+size_t scd_mstep_workspace_bytes(int64_t N, int K) { return align_up(SortWs::ints(N, std::max(K, 0)) * sizeof(int), 256) + 256; }
 
 int scd_label_histogram(const int64_t* labels, int64_t N, int K, int32_t* counts, scd_stream_t stream) {
   if (N < 0 || K <= 0) return fail("scd_label_histogram: bad shape N=%lld K=%d", (long long)N, K);
-  if (K * sizeof(int) > 48 * 1024) return fail("scd_label_histogram: K=%d too large for the shared-memory histogram", K);
+  if (K > kMaxSortK) return fail("scd_label_histogram: K=%d too large for the shared-memory histogram", K);
   if (!counts || (N > 0 && !labels)) return fail("scd_label_histogram: null pointer");
   cudaStream_t st = as_stream(stream);
   SCD_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)K, st));
@@ -375,15 +424,18 @@ int scd_mstep_sums(const float* X, const int64_t* labels, int64_t N, int D, int 
   if (N < 0 || D <= 0 || K <= 0) return fail("scd_mstep_sums: bad shape N=%lld D=%d K=%d", (long long)N, D, K);
   if (N >= (1ll << 31)) return fail("scd_mstep_sums: N=%lld exceeds the int32 row-index range", (long long)N);
   const bool vec_ok = D % 4 == 0 && D <= 128 * scd::kSegMaxVec + 124 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
-  if (K * sizeof(int) > 48 * 1024) return fail("scd_mstep_sums: K=%d too large for the shared-memory histogram", K);
+  if (K > kMaxSortK) return fail("scd_mstep_sums: K=%d too large for the shared-memory histogram", K);
   if (!sums || !counts || !ws) return fail("scd_mstep_sums: null pointer");
   if (ws_bytes < scd_mstep_workspace_bytes(N, K)) return fail("scd_mstep_sums: workspace too small (%zu < %zu)", ws_bytes, scd_mstep_workspace_bytes(N, K));
   cudaStream_t st = as_stream(stream);
-  int* offsets = reinterpret_cast<int*>(ws);
-  int* cursor = offsets + K + 1;
-  int* order = cursor + K;
-  SCD_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * (size_t)K * D, st));
-  if (int e = sort_rows_by_label(labels, N, K, counts, offsets, cursor, order, st)) return e;
+  const SortWs w(ws, K);
+  const size_t n_sums = (size_t)K * D;
+  const bool zero_in_kernel = n_sums % 4 == 0 && (reinterpret_cast<uintptr_t>(sums) & 15) == 0;
+  if (!zero_in_kernel) SCD_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * n_sums, st));
+  if (int e = sort_rows_by_label<long long>(reinterpret_cast<const long long*>(labels), 1, N, K, counts, w, zero_in_kernel ? sums : nullptr,
+                                            zero_in_kernel ? n_sums : 0, st)) return e;
+  const int* order = w.order;
+  const int* offsets = w.offsets;
   if (N > 0 && vec_ok) {
     const long long warps = (N + scd::kSegRows - 1) / scd::kSegRows;
     const long long blocks = (warps * 32 + 255) / 256;
@@ -409,13 +461,25 @@ int scd_pack_counts_inertia(const int32_t* counts, const double* inertia, int K,
 }
 
 int scd_finalize_centers(const float* sums, const int32_t* counts, const float* counts_f, const float* C_old, float* C_new,
-                         float* shift, int K, int D, void* ws, size_t ws_bytes, scd_stream_t stream) {
+                         float* shift, int K, int D, void* ws, size_t ws_bytes, void* estep_ws, size_t estep_ws_bytes,
+                         scd_stream_t stream) {
   if (K <= 0 || D <= 0) return fail("scd_finalize_centers: bad shape");
   if (!sums || (!counts && !counts_f) || !C_new) return fail("scd_finalize_centers: null pointer");
-  if (shift && (!C_old || !ws || ws_bytes < sizeof(float) * (size_t)K)) return fail("scd_finalize_centers: shift needs C_old and K floats of workspace");
+  if (shift && (!C_old || !ws)) return fail("scd_finalize_centers: shift needs C_old and K floats of workspace");
+  if (ws && ws_bytes < sizeof(float) * (size_t)K) return fail("scd_finalize_centers: workspace too small (K floats)");
+  if (estep_ws && estep_ws_bytes < scd_estep_workspace_bytes(K, D)) return fail("scd_finalize_centers: estep workspace too small");
   cudaStream_t st = as_stream(stream);
-  float* norms = shift ? reinterpret_cast<float*>(ws) : nullptr;
-  scd::finalize_centers_kernel<<<K, 256, 0, st>>>(sums, counts_f, counts, C_old, C_new, norms, K, D);
+  float* norms = (ws && C_old) ? reinterpret_cast<float*>(ws) : nullptr;
+  __nv_bfloat16 *chi = nullptr, *clo = nullptr;
+  float* cnorm = nullptr;
+  if (estep_ws) {                       // same carving as scd_estep
+    uint8_t* w8 = reinterpret_cast<uint8_t*>(estep_ws);
+    const size_t plane = align_up((size_t)K * D * 2, 256);
+    chi = reinterpret_cast<__nv_bfloat16*>(w8);
+    clo = reinterpret_cast<__nv_bfloat16*>(w8 + plane);
+    cnorm = reinterpret_cast<float*>(w8 + 2 * plane);
+  }
+  scd::finalize_centers_kernel<<<K, 256, 0, st>>>(sums, counts_f, counts, C_old, C_new, norms, K, D, chi, clo, cnorm);
   SCD_LAUNCH_CHECK("finalize_centers_kernel");
   if (shift) {
     scd::sum_small_kernel<<<1, 1024, 0, st>>>(norms, K, shift);
@@ -514,6 +578,7 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
   p.prof = g_name_prof;
   p.x = reinterpret_cast<const __nv_bfloat16*>(X);
   p.d = D;
+  p.wait_hint_ns = name_wait_hint_ns();
   if (pl.n_vsplit > 1) SCD_CUDA(cudaMemsetAsync(p.part_idx, 0xFF, pl.idx_bytes, st));   // -1: "row has nothing in this part"
 
   int e = 0;
@@ -543,60 +608,71 @@ int scd_topk_merge(const float* part_vals, const int64_t* part_idx, const float*
   return 0;
 }
 
-// workspace layout (ints): counts[K] | offsets[K+1] | cursor[K] | order[N]
+// workspace layout (ints): counts[K] | the sort workspace (offsets[K+1] | cursor[K] | acc[K] | ticket | order[N])
 size_t scd_vote_workspace_bytes(int64_t N, int K) {
-  return align_up((size_t)(3 * (size_t)K + 1 + (size_t)std::max<int64_t>(N, 0)) * sizeof(int), 256) + 256;
+  return align_up(((size_t)std::max(K, 0) + SortWs::ints(N, std::max(K, 0))) * sizeof(int), 256) + 256;
 }
 
-static int launch_vote(const int64_t* topk_idx, int k_total, int k_used, const int* order, const int* offsets, int K,
-                       const int64_t* excluded, int n_excluded, int M, int64_t* out_names, int32_t* out_counts,
-                       int32_t* out_distinct, int32_t* overflow, cudaStream_t st) {
-  SCD_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), st));
-  static bool attr_set[kMaxDevices] = {};
-  const int dev = current_device_slot();
-  if (!attr_set[dev]) {
-    SCD_CUDA(cudaFuncSetAttribute(scd::vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scd::kVoteSmemBytes));
-    attr_set[dev] = true;
-  }
-  scd::vote_kernel<<<K, scd::kVoteThreads, scd::kVoteSmemBytes, st>>>(
-      reinterpret_cast<const long long*>(topk_idx), k_total, k_used, order, offsets, K, reinterpret_cast<const long long*>(excluded),
-      n_excluded, M, reinterpret_cast<long long*>(out_names), out_counts, out_distinct, overflow);
-  SCD_LAUNCH_CHECK("vote_kernel");
-  return 0;
-}
+size_t scd_vote_spill_bytes(int64_t N, int k_used) { return scd::vote_spill_bytes(std::max<int64_t>(N, 0), std::max(k_used, 1)); }
 
 int scd_vote(const int64_t* topk_idx, int k_total, int k_used, const int64_t* cluster_of_row, int64_t N, int K,
              const int64_t* excluded, int n_excluded, int M, int64_t* out_names, int32_t* out_counts, int32_t* out_distinct,
-             int32_t* out_rows, int32_t* overflow, void* ws, size_t ws_bytes, scd_stream_t stream) {
+             int32_t* out_rows, int32_t* overflow, void* ws, size_t ws_bytes, void* spill, size_t spill_bytes, scd_stream_t stream) {
   if (N < 0 || K <= 0 || k_total <= 0 || k_used <= 0 || k_used > k_total || M <= 0) return fail("scd_vote: bad arguments");
-  if (N * (int64_t)k_used >= (1ll << 32)) return fail("scd_vote: N * k_used exceeds the 32-bit position range");
-  if (K * sizeof(int) > 48 * 1024) return fail("scd_vote: K=%d too large", K);
+  if (N * (int64_t)k_used >= (1ll << 31)) return fail("scd_vote: N * k_used exceeds the 31-bit position range");
+  if (K > kMaxSortK) return fail("scd_vote: K=%d too large", K);
   if (!topk_idx || !cluster_of_row || !out_names || !out_counts || !out_distinct || !out_rows || !overflow || !ws) return fail("scd_vote: null pointer");
   if (n_excluded > 0 && !excluded) return fail("scd_vote: excluded list is null");
   if (ws_bytes < scd_vote_workspace_bytes(N, K)) return fail("scd_vote: workspace too small");
   cudaStream_t st = as_stream(stream);
   int* counts = reinterpret_cast<int*>(ws);
-  int* offsets = counts + K;
-  int* cursor = offsets + K + 1;
-  int* order = cursor + K;
-  if (int e = sort_rows_by_label(cluster_of_row, N, K, counts, offsets, cursor, order, st)) return e;
-  SCD_CUDA(cudaMemcpyAsync(out_rows, counts, sizeof(int) * (size_t)K, cudaMemcpyDeviceToDevice, st));
-  return launch_vote(topk_idx, k_total, k_used, order, offsets, K, excluded, n_excluded, M, out_names, out_counts, out_distinct,
-                     overflow, st);
+  const SortWs w(counts + K, K);
+  if (int e = sort_rows_by_label<long long>(reinterpret_cast<const long long*>(cluster_of_row), 1, N, K, out_rows, w, nullptr, 0, st)) return e;
+  return launch_vote<long long>(reinterpret_cast<const long long*>(topk_idx), k_total, k_used, N, w.order, w.offsets, K, excluded, n_excluded,
+                                M, out_names, out_counts, out_distinct, overflow, spill, spill_bytes, st);
 }
 
 int scd_vote_presorted(const int64_t* topk_idx, int k_total, int k_used, const void* mstep_ws, int64_t N, int K,
                        const int64_t* excluded, int n_excluded, int M, int64_t* out_names, int32_t* out_counts,
-                       int32_t* out_distinct, int32_t* overflow, scd_stream_t stream) {
+                       int32_t* out_distinct, int32_t* overflow, void* spill, size_t spill_bytes, scd_stream_t stream) {
   if (N < 0 || K <= 0 || k_total <= 0 || k_used <= 0 || k_used > k_total || M <= 0) return fail("scd_vote_presorted: bad arguments");
-  if (N * (int64_t)k_used >= (1ll << 32)) return fail("scd_vote_presorted: N * k_used exceeds the 32-bit position range");
+  if (N * (int64_t)k_used >= (1ll << 31)) return fail("scd_vote_presorted: N * k_used exceeds the 31-bit position range");
   if (!topk_idx || !mstep_ws || !out_names || !out_counts || !out_distinct || !overflow) return fail("scd_vote_presorted: null pointer");
   if (n_excluded > 0 && !excluded) return fail("scd_vote_presorted: excluded list is null");
-  // layout written by scd_mstep_sums: offsets[K+1] | cursor[K] | order[N]
-  const int* offsets = reinterpret_cast<const int*>(mstep_ws);
-  const int* order = offsets + 2 * K + 1;
-  return launch_vote(topk_idx, k_total, k_used, order, offsets, K, excluded, n_excluded, M, out_names, out_counts, out_distinct,
-                     overflow, as_stream(stream));
+  const SortWs w(const_cast<void*>(mstep_ws), K);         // as written by scd_mstep_sums
+  return launch_vote<long long>(reinterpret_cast<const long long*>(topk_idx), k_total, k_used, N, w.order, w.offsets, K, excluded, n_excluded,
+                                M, out_names, out_counts, out_distinct, overflow, spill, spill_bytes, as_stream(stream));
+}
+
+int scd_pack_vote_records(const int64_t* labels, const int64_t* topk_idx, int k_total, int k_used, int64_t n, int32_t* rec,
+                          scd_stream_t stream) {
+  if (n < 0 || k_total <= 0 || k_used <= 0 || k_used > k_total) return fail("scd_pack_vote_records: bad arguments");
+  if (n == 0) return 0;
+  if (!labels || !topk_idx || !rec) return fail("scd_pack_vote_records: null pointer");
+  const long long total = n * (1 + k_used);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  scd::pack_vote_records_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(labels),
+                                                                       reinterpret_cast<const long long*>(topk_idx), k_total, k_used, n, rec);
+  SCD_LAUNCH_CHECK("pack_vote_records_kernel");
+  return 0;
+}
+
+int scd_vote_records(const int32_t* rec, int k_used, int64_t N, int K, const int64_t* excluded, int n_excluded, int M,
+                     int64_t* out_names, int32_t* out_counts, int32_t* out_distinct, int32_t* out_rows, int32_t* overflow,
+                     void* ws, size_t ws_bytes, void* spill, size_t spill_bytes, scd_stream_t stream) {
+  if (N < 0 || K <= 0 || k_used <= 0 || M <= 0) return fail("scd_vote_records: bad arguments");
+  if (N * (int64_t)k_used >= (1ll << 31)) return fail("scd_vote_records: N * k_used exceeds the 31-bit position range");
+  if (K > kMaxSortK) return fail("scd_vote_records: K=%d too large", K);
+  if (!rec || !out_names || !out_counts || !out_distinct || !out_rows || !overflow || !ws) return fail("scd_vote_records: null pointer");
+  if (n_excluded > 0 && !excluded) return fail("scd_vote_records: excluded list is null");
+  if (ws_bytes < scd_vote_workspace_bytes(N, K)) return fail("scd_vote_records: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  int* counts = reinterpret_cast<int*>(ws);
+  const SortWs w(counts + K, K);
+  const long long stride = 1 + k_used;
+  if (int e = sort_rows_by_label<int>(rec, stride, N, K, out_rows, w, nullptr, 0, st)) return e;
+  return launch_vote<int>(rec + 1, stride, k_used, N, w.order, w.offsets, K, excluded, n_excluded, M, out_names, out_counts, out_distinct,
+                          overflow, spill, spill_bytes, st);
 }
 
 int scd_contingency(const void* y_pred, int pred_is_f64, const void* y_true, int true_is_f64, int64_t N, int D,

@@ -5,7 +5,11 @@ the GPUs, gloo in the CPU tests) for the two exchange steps the path really has:
     iteration (``scd_b200.kmeans.K_Means(process_group=...)``);
   * naming: vocabulary column-sharded, local fused top-k per rank (global column indices), all-gather of
     the ``[N, k]`` (value, index) lists (+ per-row max / sum-exp when the softmax is wanted) and a k-way
-    merge kernel.  Row-sharded naming needs no exchange at all.
+    merge kernel.  Row-sharded naming needs no exchange at all;
+  * vote: each rank packs its rows' ``[label, name_0 .. name_(k-1)]`` into int32 records, ONE all-gather
+    (``RowGather``) replicates them and every rank runs the exact vote on the gathered records
+    (``sharded_vote``).  Per-cluster name histograms are sparse and unbounded, so "histograms add" is done
+    by gathering the 24-byte rows, not K x V dense tables.
 """
 from __future__ import annotations
 
@@ -31,6 +35,19 @@ def allreduce_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
     return packed
 
 
+def all_gather_into(out: torch.Tensor, inp: torch.Tensor, group=None):
+    """``dist.all_gather_into_tensor`` (NCCL on the GPUs).  gloo has no all-gather for CUDA tensors - the multi-rank
+    tests that share one GPU stage through the host there."""
+    import torch.distributed as dist
+    if inp.is_cuda and dist.get_backend(group) == 'gloo':
+        host = torch.empty(out.shape, dtype=out.dtype)
+        dist.all_gather_into_tensor(host, inp.cpu().contiguous(), group=group)
+        out.copy_(host)
+        return out
+    dist.all_gather_into_tensor(out, inp, group=group)
+    return out
+
+
 class RowGather:
     """All-gather of row-sharded per-row results (labels ``[n]``, top-k indices ``[n, k]``) into the full
     ``[N, ...]`` tensor on every rank.  Shards are the ceil-sized blocks of ``shard_bounds``; the ragged last
@@ -52,7 +69,7 @@ class RowGather:
 
     def gather(self):
         import torch.distributed as dist
-        dist.all_gather_into_tensor(self.full_padded, self.local_padded, group=self.group)
+        all_gather_into(self.full_padded, self.local_padded, self.group)
         return self.full
 
 
@@ -96,12 +113,30 @@ def sharded_score_topk(feats_bf16: torch.Tensor, vocab_shard, k: int, softmax: b
         return merge_topk_stacked(vals.unsqueeze(0), idx.unsqueeze(0), rmax.unsqueeze(0), rsum.unsqueeze(0), k, softmax, scale)
     gv = torch.empty((world,) + tuple(vals.shape), dtype=vals.dtype, device=vals.device)
     gi = torch.empty((world,) + tuple(idx.shape), dtype=idx.dtype, device=idx.device)
-    dist.all_gather_into_tensor(gv, vals, group=group)
-    dist.all_gather_into_tensor(gi, idx, group=group)
+    all_gather_into(gv, vals, group)
+    all_gather_into(gi, idx, group)
     gm = gs = None
     if softmax:
         gm = torch.empty((world,) + tuple(rmax.shape), dtype=rmax.dtype, device=rmax.device)
         gs = torch.empty((world,) + tuple(rsum.shape), dtype=rsum.dtype, device=rsum.device)
-        dist.all_gather_into_tensor(gm, rmax, group=group)
-        dist.all_gather_into_tensor(gs, rsum, group=group)
+        all_gather_into(gm, rmax, group)
+        all_gather_into(gs, rsum, group)
     return merge_topk_stacked(gv, gi, gm, gs, k, softmax, scale)
+
+
+def grid_2d(world: int, rank: int, vocab_ways: int):
+    """Rank -> (row group, vocabulary group) of a ``(world // vocab_ways) x vocab_ways`` process grid: ranks that
+    share a row block are consecutive, so the all-gather of their partial top-k lists stays inside the group."""
+    if vocab_ways < 1 or world % vocab_ways:
+        raise ValueError(f'vocab_ways={vocab_ways} does not divide the world size {world}')
+    return rank // vocab_ways, rank % vocab_ways
+
+
+def sharded_vote(labels_local: torch.Tensor, idx_local: torch.Tensor, top_k: int, n_clusters: int, num_common: int,
+                 gather: 'RowGather', plan=None, known_name_idx=None):
+    """Row-sharded vote: pack this rank's records into ``gather.local`` (``RowGather(n_total, (1 + top_k,), int32)``),
+    all-gather once, vote on the gathered records.  Every rank returns the full result of ``naming.vote_device``."""
+    from . import naming
+    naming.pack_vote_records(labels_local, idx_local, top_k, out=gather.local)
+    records = gather.gather()
+    return naming.vote_records(records, n_clusters, num_common, known_name_idx=known_name_idx, plan=plan)

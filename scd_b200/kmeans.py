@@ -11,7 +11,12 @@ the current CUDA device and results are returned on the input's device.  No CPU 
 
 Sharded use (rows of ``X`` / ``u_feats`` block-sharded over the ranks of a ``torch.distributed``
 process group, one process per GPU): pass ``process_group=`` - the M-step then all-reduces one packed
-``[K*D sums | K counts | inertia]`` fp32/fp64 buffer per iteration over NCCL.
+``[K*D sums | K counts | inertia]`` fp32 buffer per iteration over NCCL.  Everything that
+decides the result is made identical on every rank: the host RNG is re-seeded from a seed rank 0 draws and
+broadcasts, k-means++ draws over the GLOBAL distance mass (all-gathered shard sums pick the owning rank, which
+resolves the row on its device and broadcasts it), the 'random' / first-k initialisations take GLOBAL row
+indices, and the labelled rows of ``fit_mix`` (``l_feats`` / ``l_targets`` are REPLICATED on every rank) enter
+the all-reduced sums once, through rank 0.  ``labels_`` holds the labels of the rank's own rows.
 """
 from __future__ import annotations
 
@@ -36,18 +41,41 @@ def _dev_f32(t: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- thin kernel wrappers
+class _EStep:
+    """Workspace of the tensor-core E-step for a fixed ``(K, D)``: the centroid hi / lo planes and norms.  One per
+    fit (or per cached ``(K, D, device, stream)``), never shared between streams.  ``ready_for`` remembers the
+    centre tensor whose operands ``_MStep.finalize(estep=...)`` has already left in the workspace."""
+
+    def __init__(self, k, d, device):
+        lib = _lib.load()
+        self.k, self.d = int(k), int(d)
+        self.ws = torch.empty(lib.scd_estep_workspace_bytes(self.k, self.d), dtype=torch.uint8, device=device)
+        self.ready_for = None
+
+    def run(self, X, C, labels_out, inertia_acc, mindist=None, exact=False):
+        lib = _lib.load()
+        flags = _lib.ESTEP_EXACT if exact else 0
+        if self.ready_for is not None and self.ready_for == C.data_ptr():
+            flags |= _lib.ESTEP_PLANES_READY
+        self.ready_for = None
+        _lib.check(lib.scd_estep(X.data_ptr(), X.shape[0], X.shape[1], C.data_ptr(), C.shape[0],
+                                 labels_out.data_ptr(), _lib.ptr(mindist), _lib.ptr(inertia_acc), flags,
+                                 self.ws.data_ptr(), self.ws.numel(), _stream()), 'scd_estep')
+
+
 _ESTEP_WS = {}
 
 
 def _estep(X, C, labels_out, inertia_acc, mindist=None, exact=False):
-    lib = _lib.load()
-    key = (int(C.shape[0]), int(C.shape[1]), X.device.index)
-    ws = _ESTEP_WS.get(key)
-    if ws is None:
-        ws = _ESTEP_WS[key] = torch.empty(lib.scd_estep_workspace_bytes(key[0], key[1]), dtype=torch.uint8, device=X.device)
-    _lib.check(lib.scd_estep(X.data_ptr(), X.shape[0], X.shape[1], C.data_ptr(), C.shape[0],
-                             labels_out.data_ptr(), _lib.ptr(mindist), _lib.ptr(inertia_acc), int(bool(exact)),
-                             ws.data_ptr(), ws.numel(), _stream()), 'scd_estep')
+    """One-off E-step (predict, seeding, tests): workspace cached per (K, D, device, stream)."""
+    key = (int(C.shape[0]), int(C.shape[1]), X.device.index, _stream())
+    es = _ESTEP_WS.get(key)
+    if es is None:
+        if len(_ESTEP_WS) > 64:
+            _ESTEP_WS.clear()
+        es = _ESTEP_WS[key] = _EStep(key[0], key[1], X.device)
+    es.ready_for = None
+    es.run(X, C, labels_out, inertia_acc, mindist, exact)
 
 
 class _MStep:
@@ -56,26 +84,34 @@ class _MStep:
     def __init__(self, n, d, k, device):
         lib = _lib.load()
         self.n, self.d, self.k = n, d, k
-        self.ws = torch.empty(lib.scd_mstep_workspace_bytes(n, k), dtype=torch.uint8, device=device)
+        self.ws = torch.zeros(lib.scd_mstep_workspace_bytes(n, k), dtype=torch.uint8, device=device)
         # one buffer [K*D sums | K counts | inertia] (fp32) so the row-sharded case all-reduces it in one call
         self.packed = torch.zeros(k * d + k + 1, dtype=torch.float32, device=device)
         self.sums = self.packed[:k * d].view(k, d)
         self.counts_f = self.packed[k * d:k * d + k]
         self.counts = torch.empty(k, dtype=torch.int32, device=device)
-        self.norm_ws = torch.empty(max(k, 1), dtype=torch.float32, device=device)
+        self.norms = torch.zeros(max(k, 1), dtype=torch.float32, device=device)     # ||c_new[k] - c_old[k]||
         self.shift = torch.zeros(1, dtype=torch.float32, device=device)
+        self.tc = bool(lib.scd_estep_uses_tensor_cores(max(n, 1), d, k))
 
     def sums_counts(self, X, labels):
         lib = _lib.load()
         _lib.check(lib.scd_mstep_sums(X.data_ptr(), labels.data_ptr(), self.n, self.d, self.k, self.sums.data_ptr(),
                                       self.counts.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _stream()), 'scd_mstep_sums')
 
-    def finalize(self, c_old, c_new, counts_f=None):
+    def finalize(self, c_old, c_new, counts_f=None, estep: '_EStep | None' = None, shift=True):
+        """divide (+ per-cluster move norms when ``c_old`` is given; ``shift=True`` also sums them on the device into
+        ``self.shift``).  ``estep``: leave the next E-step's operands of ``c_new`` in that plan's workspace."""
         lib = _lib.load()
+        want_shift = shift and c_old is not None
         _lib.check(lib.scd_finalize_centers(self.sums.data_ptr(), None if counts_f is not None else self.counts.data_ptr(),
                                             _lib.ptr(counts_f), _lib.ptr(c_old), c_new.data_ptr(),
-                                            self.shift.data_ptr() if c_old is not None else None, self.k, self.d,
-                                            self.norm_ws.data_ptr(), self.norm_ws.numel() * 4, _stream()), 'scd_finalize_centers')
+                                            self.shift.data_ptr() if want_shift else None, self.k, self.d,
+                                            self.norms.data_ptr(), self.norms.numel() * 4,
+                                            estep.ws.data_ptr() if estep is not None else None,
+                                            estep.ws.numel() if estep is not None else 0, _stream()), 'scd_finalize_centers')
+        if estep is not None:
+            estep.ready_for = c_new.data_ptr()
 
 
 def pairwise_distance(data1, data2, batch_size=None, *, out_device=None):
@@ -138,7 +174,44 @@ class K_Means:
         self.mode = mode
         self.process_group = process_group
 
-    # ------------------------------------------------------------------ helpers
+    # ------------------------------------------------------------------ sharding helpers
+    def _world(self):
+        if self.process_group is None:
+            return 1, 0
+        import torch.distributed as dist
+        return dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
+
+    def _shard_layout(self, n_local, device):
+        """Global row offsets of every rank's shard (``[world + 1]`` Python ints) - one all-gather of the local sizes."""
+        world, _ = self._world()
+        if world == 1:
+            return [0, n_local]
+        from . import dist as sdist
+        sizes = torch.zeros(world, dtype=torch.int64, device=device)
+        sdist.all_gather_into(sizes, torch.tensor([n_local], dtype=torch.int64, device=device), self.process_group)
+        offs = [0]
+        for v in sizes.tolist():
+            offs.append(offs[-1] + int(v))
+        return offs
+
+    def _global_rows(self, Xd, global_idx):
+        """``X_global[global_idx]`` on every rank when the rows of X are block-sharded: the owner of each index fills
+        its row of a zero buffer, one all-reduce (sum) replicates the lot."""
+        world, rank = self._world()
+        idx = [int(i) for i in np.asarray(global_idx).reshape(-1)]
+        if world == 1:
+            return Xd[torch.as_tensor(idx, device=Xd.device, dtype=torch.int64)].clone()
+        import torch.distributed as dist
+        offs = self._shard_layout(int(Xd.shape[0]), Xd.device)
+        out = torch.zeros(len(idx), Xd.shape[1], dtype=torch.float32, device=Xd.device)
+        mine = [(j, g - offs[rank]) for j, g in enumerate(idx) if offs[rank] <= g < offs[rank + 1]]
+        if mine:
+            dst = torch.as_tensor([j for j, _ in mine], device=Xd.device, dtype=torch.int64)
+            src = torch.as_tensor([r for _, r in mine], device=Xd.device, dtype=torch.int64)
+            out[dst] = Xd[src]
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.process_group)
+        return out
+
     def _allreduce(self, mstep: _MStep, inertia_acc: torch.Tensor):
         """one packed all-reduce of [K*D sums | K counts | inertia] when rows are sharded."""
         if self.process_group is None:
@@ -151,10 +224,13 @@ class K_Means:
         inertia_acc.copy_(mstep.packed[-1:])
         return mstep.counts_f
 
-    def _assign(self, X, centers, labels_out, inertia_acc):
+    def _assign(self, X, centers, labels_out, inertia_acc, estep: '_EStep | None' = None):
         """E-step of one iteration: ``labels_out[i] = argmin_k ||X_i - c_k||^2`` and ``inertia_acc += sum of the
         minima``.  (The size-constrained subclass overrides this with the min-cost-flow assignment.)"""
-        _estep(X, centers, labels_out, inertia_acc)
+        if estep is not None:
+            estep.run(X, centers, labels_out, inertia_acc)
+        else:
+            _estep(X, centers, labels_out, inertia_acc)
 
     def _lloyd(self, X_assign, X_all, labels, l_num, centers, l_feats=None):
         """The iteration loop shared by fit_once (:56-74) and fit_mix_once (:102-126).
@@ -164,10 +240,13 @@ class K_Means:
         dev = X_all.device
         k, d = self.k, X_all.shape[1]
         mstep = _MStep(X_all.shape[0], d, k, dev)
+        estep = _EStep(k, d, dev)
         inertia_acc = torch.zeros(1, dtype=torch.float64, device=dev)
         c_cur = centers.clone().contiguous()
         c_new = torch.empty_like(c_cur)
-        host = torch.empty(2, dtype=torch.float64).pin_memory()
+        # inertia and the K move norms leave the device as two small pinned copies: the one host sync per iteration
+        host_i = torch.empty(1, dtype=torch.float64).pin_memory()
+        host_n = torch.empty(mstep.norms.numel(), dtype=torch.float32).pin_memory()
         best_labels = best_inertia = best_centers = None
         n_done = 0
         u_view = labels[l_num:]
@@ -175,18 +254,22 @@ class K_Means:
             n_done = it + 1
             inertia_acc.zero_()
             if X_assign.shape[0]:
-                self._assign(X_assign, c_cur, u_view, inertia_acc)                 # :58-60 / :105-107,:111
+                self._assign(X_assign, c_cur, u_view, inertia_acc, estep)          # :58-60 / :105-107,:111
             if l_num:
                 lib = _lib.load()
                 _lib.check(lib.scd_labelled_inertia(l_feats.data_ptr(), labels.data_ptr(), l_num, d, c_cur.data_ptr(), k,
                                                     inertia_acc.data_ptr(), _stream()), 'scd_labelled_inertia')   # :108-110
             mstep.sums_counts(X_all, labels)                                       # :61-64 / :113-116
             counts_f = self._allreduce(mstep, inertia_acc)
-            mstep.finalize(c_cur, c_new, counts_f)                                 # divide + :71 / :123
-            host[0:1].copy_(inertia_acc, non_blocking=True)
-            host[1:2].copy_(mstep.shift.double(), non_blocking=True)
+            mstep.finalize(c_cur, c_new, counts_f, estep=estep if mstep.tc else None, shift=False)   # divide + :71 / :123
+            host_i.copy_(inertia_acc, non_blocking=True)
+            host_n.copy_(mstep.norms, non_blocking=True)
             torch.cuda.current_stream().synchronize()                              # the one host sync per iteration
-            inertia, shift = float(host[0]), float(host[1])
+            inertia = float(host_i[0])
+            # :71 / :123 torch.sum(torch.sqrt(...)) in fp32: the K norms are added in a fixed order on the host
+            shift = np.float32(0.0)
+            for v in host_n.numpy()[:k]:
+                shift = np.float32(shift + v)
             inertia32 = float(np.float32(inertia))
             if best_inertia is None or inertia32 < best_inertia:                   # :66-69 / :118-121
                 best_labels, best_centers, best_inertia = labels.clone(), c_new.clone(), inertia32
@@ -202,9 +285,13 @@ class K_Means:
         (``scd_kpp_update``: one N x D pass per centre instead of the reference's N x c x D); draws
         ``r = random_state.rand()`` from the same host RNG stream, one draw per centre, and resolves
         ``first index with cumsum(d2 / sum(d2)) >= r`` on the device (``scd_kpp_select``).  The picked row index
-        stays on the device, so the whole seeding is a stream of launches with a single host sync at the end."""
+        stays on the device, so the whole seeding is a stream of launches with a single host sync at the end.
+        With ``process_group`` the rows of ``X`` are this rank's shard and the draw runs over the global distance
+        mass (``_kpp_sharded``); ``pre_centers`` must then be identical on every rank."""
         rs = check_random_state(random_state)
         Xd = _dev_f32(X)
+        if self._world()[0] > 1:
+            return self._kpp_sharded(Xd, pre_centers, k, rs)
         n, d = int(Xd.shape[0]), int(Xd.shape[1])
         dev = Xd.device
         if pre_centers is not None:
@@ -229,13 +316,74 @@ class K_Means:
             r = float(rs.rand())                                                   # :33 (one host draw per added centre)
             _lib.check(lib.scd_kpp_select(d2.data_ptr(), n, sums_valid, r, pick.data_ptr(), no_hit.data_ptr(), ws.data_ptr(),
                                           ws.numel(), _stream()), 'scd_kpp_select')                          # :31-34
-            _lib.check(lib.scd_kpp_update(Xd.data_ptr(), n, d, pick.data_ptr(), 0, d2.data_ptr(), centers[n_have].data_ptr(),
+            _lib.check(lib.scd_kpp_update(Xd.data_ptr(), n, d, pick.data_ptr(), None, 0, d2.data_ptr(), centers[n_have].data_ptr(),
                                           ws.data_ptr(), ws.numel(), _stream()), 'scd_kpp_update')           # :35 + next :28-30
             sums_valid = 1
             n_have += 1
         if int(no_hit.item()) & 2:                                                 # the one host sync of the seeding
             # gcd copy :104-107 silently reuses the previous index; with none yet, both copies fail
             raise IndexError('kpp: no cumulative probability reached the draw (reference :34)')
+        return centers[:n_have]
+
+    def _kpp_sharded(self, Xd, pre_centers, k, rs):
+        """k-means++ over block-sharded rows.  Every rank holds the same RNG state.  Per added centre: the
+        shard sums of the min-distance vector are all-gathered (fp64), the draw ``r * total`` falls into exactly one
+        shard, that rank resolves the row on its device with the remaining mass as its local draw and broadcasts the
+        row; every rank then updates its own min-distance vector against the broadcast vector.  One small host sync
+        per centre (the reference syncs per centre as well, :34 ``.nonzero()[0][0]``)."""
+        import torch.distributed as dist
+        from . import dist as sdist
+        lib = _lib.load()
+        group = self.process_group
+        world, rank = self._world()
+        n, d = int(Xd.shape[0]), int(Xd.shape[1])
+        dev = Xd.device
+        offs = self._shard_layout(n, dev)
+        if pre_centers is not None:
+            Cc = _dev_f32(pre_centers).view(-1, d)
+        else:
+            Cc = self._global_rows(Xd, [rs.randint(0, offs[-1])]).view(1, -1)      # :25 over the global row range
+        centers = torch.empty(max(k, Cc.shape[0]), d, dtype=torch.float32, device=dev)
+        n_have = int(Cc.shape[0])
+        centers[:n_have] = Cc
+        if n_have >= k:
+            return centers[:n_have]
+        ws = torch.empty(lib.scd_kpp_workspace_bytes(max(n, 1)), dtype=torch.uint8, device=dev)
+        d2 = torch.zeros(max(n, 1), dtype=torch.float32, device=dev)
+        pick = torch.full((1,), -1, dtype=torch.int64, device=dev)
+        no_hit = torch.zeros(1, dtype=torch.int32, device=dev)
+        if n:
+            _estep(Xd, centers[:n_have].contiguous(), torch.empty(n, dtype=torch.int64, device=dev), None, mindist=d2, exact=True)
+        sums = torch.zeros(world, dtype=torch.float64, device=dev)
+        row = torch.empty(d, dtype=torch.float32, device=dev)
+        while n_have < k:
+            r = float(rs.rand())                                                   # :33, the same value on every rank
+            local = d2[:n].double().sum().view(1) if n else torch.zeros(1, dtype=torch.float64, device=dev)
+            sdist.all_gather_into(sums, local, group)
+            shard = sums.tolist()
+            total = float(sum(shard))
+            if not total > 0.0:
+                raise IndexError('kpp: no cumulative probability reached the draw (reference :34)')
+            target, run, owner = r * total, 0.0, world - 1
+            for q in range(world):
+                if shard[q] > 0.0 and run + shard[q] >= target:
+                    owner = q
+                    break
+                run += shard[q]
+            if rank == owner:
+                r_local = min(max((target - run) / shard[owner], 0.0), 1.0)
+                pick.fill_(-1)
+                _lib.check(lib.scd_kpp_select(d2.data_ptr(), n, 0, r_local, pick.data_ptr(), no_hit.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), _stream()), 'scd_kpp_select')
+                p_host = int(pick.item())
+                row.copy_(Xd[p_host if p_host >= 0 else n - 1])                    # rounding at the shard's far end: its last row
+            src = dist.get_global_rank(group, owner) if group is not None else owner
+            dist.broadcast(row, src=src, group=group)
+            centers[n_have] = row
+            if n:
+                _lib.check(lib.scd_kpp_update(Xd.data_ptr(), n, d, None, row.data_ptr(), 0, d2.data_ptr(), None,
+                                              ws.data_ptr(), ws.numel(), _stream()), 'scd_kpp_update')
+            n_have += 1
         return centers[:n_have]
 
     def fit_once(self, X, random_state):
@@ -245,10 +393,13 @@ class K_Means:
             centers = self.kpp(Xd, k=k, random_state=random_state)                 # :44
         elif self.init == 'random':
             rs = check_random_state(self.random_state)                             # :46 (self.random_state, as the reference)
-            idx = rs.choice(len(Xd), k, replace=False)
-            centers = Xd[torch.as_tensor(idx, device=Xd.device)].clone()           # :47-49
+            if self._world()[0] > 1 and not isinstance(self.random_state, (int, np.integer)):
+                rs = random_state                                                   # the shared stream of _best_of: same draw on every rank
+            n_total = self._shard_layout(int(Xd.shape[0]), Xd.device)[-1]
+            idx = rs.choice(n_total, k, replace=False)
+            centers = self._global_rows(Xd, idx)                                   # :47-49
         else:
-            centers = Xd[:k].clone()                                               # :50-52
+            centers = self._global_rows(Xd, list(range(k))) if self._world()[0] > 1 else Xd[:k].clone()   # :50-52
         labels = torch.empty(Xd.shape[0], dtype=torch.int64, device=Xd.device)
         return self._lloyd(Xd, Xd, labels, 0, centers)
 
@@ -258,21 +409,37 @@ class K_Means:
         tg = tg.to(U.device)
         l_classes, remapped = torch.unique(tg, return_inverse=True)                # :80, :93-95 (sorted unique -> 0..C_l-1)
         l_num, n_lab_classes = int(tg.numel()), int(l_classes.numel())
-        cat_feats = torch.cat((L, U)).contiguous()                                 # :83
-        labels = torch.full((cat_feats.shape[0],), -1, dtype=torch.int64, device=U.device)     # :88
-        labels[:l_num] = remapped.view(-1).long()
-        # labelled class means (:78-82) with the M-step kernels
+        lab_labels = remapped.view(-1).long().contiguous()
+        # labelled class means (:78-82) with the M-step kernels (labelled rows are replicated: no exchange)
         ms = _MStep(l_num, L.shape[1], n_lab_classes, U.device)
-        ms.sums_counts(L, labels[:l_num].contiguous())
+        ms.sums_counts(L, lab_labels)
         l_centers = torch.empty(n_lab_classes, L.shape[1], dtype=torch.float32, device=U.device)
         ms.finalize(None, l_centers)
         centers = self.kpp(U, l_centers, k=self.k, random_state=random_state)      # :98
-        best_labels, best_inertia, best_centers, _ = self._lloyd(U, cat_feats, labels, l_num, centers, l_feats=L)
+        world, rank = self._world()
+        if world > 1 and rank != 0:
+            # the replicated labelled rows enter the all-reduced sums / inertia once, through rank 0
+            u_labels = torch.full((U.shape[0],), -1, dtype=torch.int64, device=U.device)
+            best_u, best_inertia, best_centers, _ = self._lloyd(U, U, u_labels, 0, centers)
+            best_labels = torch.cat((lab_labels, best_u))
+        else:
+            cat_feats = torch.cat((L, U)).contiguous()                             # :83
+            labels = torch.full((cat_feats.shape[0],), -1, dtype=torch.int64, device=U.device)     # :88
+            labels[:l_num] = lab_labels
+            best_labels, best_inertia, best_centers, _ = self._lloyd(U, cat_feats, labels, l_num, centers, l_feats=L)
         # :127 returns the stale loop variable of :94 + 1, i.e. the number of labelled rows
         return best_labels, best_inertia, best_centers, l_num
 
     def _best_of(self, run, src_device):
         rs = check_random_state(self.random_state)
+        if self._world()[0] > 1:
+            # one RNG stream for all ranks: rank 0 draws a seed from its own state (random_state=None included) and
+            # broadcasts it - every rank then takes identical draws, so centres, labels and the `break` agree
+            import torch.distributed as dist
+            seed = torch.tensor([int(rs.randint(0, 2 ** 31 - 1))], dtype=torch.int64, device='cuda')
+            src = dist.get_global_rank(self.process_group, 0) if self.process_group is not None else 0
+            dist.broadcast(seed, src=src, group=self.process_group)
+            rs = np.random.RandomState(int(seed.item()))
         best = None
         for _ in range(self.n_init):                                               # :133-140 / :157-164
             labels, inertia, centers, n_iters = run(rs)

@@ -228,17 +228,25 @@ def reassign(feats, zeroshot_weights, cand_name_idx) -> np.ndarray:
 
 # ----------------------------------------------------------------------------------------- voting
 class VotePlan:
-    """Outputs + workspace of the device vote for fixed ``(n, K, M)``."""
+    """Outputs + workspace of the device vote for fixed ``(n, K, M)``.  ``k_used`` sizes the global-memory spill
+    tables that clusters with more than 8192 top-k entries build their name histogram in (24 bytes per entry; any
+    cluster fits, there is no distinct-name limit); it is only allocated when such a cluster can exist."""
 
-    def __init__(self, n: int, n_clusters: int, num_common: int, device):
+    def __init__(self, n: int, n_clusters: int, num_common: int, device, k_used: int = 5):
         lib = _lib.load()
-        self.n, self.K, self.M = int(n), int(n_clusters), int(num_common)
+        self.n, self.K, self.M, self.k_used = int(n), int(n_clusters), int(num_common), int(k_used)
         self.names = torch.empty(self.K, self.M, dtype=torch.int64, device=device)
         self.counts = torch.empty(self.K, self.M, dtype=torch.int32, device=device)
         self.distinct = torch.empty(self.K, dtype=torch.int32, device=device)
         self.rows = torch.empty(self.K, dtype=torch.int32, device=device)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
-        self.ws = torch.empty(lib.scd_vote_workspace_bytes(self.n, self.K), dtype=torch.uint8, device=device)
+        self.ws = torch.zeros(lib.scd_vote_workspace_bytes(self.n, self.K), dtype=torch.uint8, device=device)
+        self.spill = None
+        if self.n * self.k_used > 8192:
+            self.spill = torch.empty(lib.scd_vote_spill_bytes(self.n, self.k_used), dtype=torch.uint8, device=device)
+
+    def spill_args(self):
+        return (_lib.ptr(self.spill), 0 if self.spill is None else self.spill.numel())
 
 
 def vote_device(name_idx_topk: torch.Tensor, cluster_of_row, n_clusters: int, top_k: int, num_common: int,
@@ -257,8 +265,8 @@ def vote_device(name_idx_topk: torch.Tensor, cluster_of_row, n_clusters: int, to
     dev = idx.device
     K, M = int(n_clusters), int(num_common)
     if plan is None:
-        plan = VotePlan(n, K, M, dev)
-    elif (plan.n, plan.K, plan.M) != (n, K, M):
+        plan = VotePlan(n, K, M, dev, k_used=int(top_k))
+    elif (plan.n, plan.K, plan.M) != (n, K, M) or plan.k_used < int(top_k):
         raise ValueError('VotePlan was built for a different shape')
     excl = None
     if known_name_idx is not None and len(known_name_idx):
@@ -270,7 +278,7 @@ def vote_device(name_idx_topk: torch.Tensor, cluster_of_row, n_clusters: int, to
         _lib.check(lib.scd_vote_presorted(idx.data_ptr(), kt, int(top_k), presorted.ws.data_ptr(), n, K, _lib.ptr(excl),
                                           0 if excl is None else int(excl.numel()), M, plan.names.data_ptr(),
                                           plan.counts.data_ptr(), plan.distinct.data_ptr(), plan.overflow.data_ptr(),
-                                          _stream()), 'scd_vote_presorted')
+                                          *plan.spill_args(), _stream()), 'scd_vote_presorted')
         return plan.names, plan.counts, plan.distinct, presorted.counts, plan.overflow
     cl = cluster_of_row
     if not (torch.is_tensor(cl) and cl.is_cuda and cl.dtype == torch.int64 and cl.is_contiguous()):
@@ -278,7 +286,38 @@ def vote_device(name_idx_topk: torch.Tensor, cluster_of_row, n_clusters: int, to
     _lib.check(lib.scd_vote(idx.data_ptr(), kt, int(top_k), cl.data_ptr(), n, K, _lib.ptr(excl),
                             0 if excl is None else int(excl.numel()), M, plan.names.data_ptr(), plan.counts.data_ptr(),
                             plan.distinct.data_ptr(), plan.rows.data_ptr(), plan.overflow.data_ptr(), plan.ws.data_ptr(),
-                            plan.ws.numel(), _stream()), 'scd_vote')
+                            plan.ws.numel(), *plan.spill_args(), _stream()), 'scd_vote')
+    return plan.names, plan.counts, plan.distinct, plan.rows, plan.overflow
+
+
+def pack_vote_records(labels: torch.Tensor, name_idx_topk: torch.Tensor, top_k: int, out: torch.Tensor | None = None):
+    """``[n, 1 + top_k]`` int32 records ``[label, name_0 .. name_(top_k-1)]`` - what a rank contributes to the ONE
+    all-gather of the row-sharded vote."""
+    n, kt = int(name_idx_topk.shape[0]), int(name_idx_topk.shape[1])
+    if out is None:
+        out = torch.empty(n, 1 + int(top_k), dtype=torch.int32, device=name_idx_topk.device)
+    lib = _lib.load()
+    _lib.check(lib.scd_pack_vote_records(labels.data_ptr(), name_idx_topk.data_ptr(), kt, int(top_k), n, out.data_ptr(), _stream()),
+               'scd_pack_vote_records')
+    return out
+
+
+def vote_records(records: torch.Tensor, n_clusters: int, num_common: int, known_name_idx=None, plan: VotePlan | None = None):
+    """The vote over gathered ``[N, 1 + top_k]`` int32 records (see ``pack_vote_records``); same outputs as ``vote_device``."""
+    n, top_k = int(records.shape[0]), int(records.shape[1]) - 1
+    K, M = int(n_clusters), int(num_common)
+    if plan is None:
+        plan = VotePlan(n, K, M, records.device, k_used=top_k)
+    elif (plan.n, plan.K, plan.M) != (n, K, M) or plan.k_used < top_k:
+        raise ValueError('VotePlan was built for a different shape')
+    excl = None
+    if known_name_idx is not None and len(known_name_idx):
+        excl = torch.as_tensor(np.asarray(list(known_name_idx), dtype=np.int64), device=records.device)
+    lib = _lib.load()
+    _lib.check(lib.scd_vote_records(records.data_ptr(), top_k, n, K, _lib.ptr(excl), 0 if excl is None else int(excl.numel()), M,
+                                    plan.names.data_ptr(), plan.counts.data_ptr(), plan.distinct.data_ptr(), plan.rows.data_ptr(),
+                                    plan.overflow.data_ptr(), plan.ws.data_ptr(), plan.ws.numel(), *plan.spill_args(), _stream()),
+               'scd_vote_records')
     return plan.names, plan.counts, plan.distinct, plan.rows, plan.overflow
 
 
@@ -295,8 +334,8 @@ def vote(name_idx_topk, u_preds, cluster_ids, top_k: int, num_common: int, known
         K = int(preds.max()) + 1
     names, counts, _, _, overflow = vote_device(name_idx_topk, preds, K, top_k, num_common, known_name_idx)
     names_h, counts_h, ovf = names.cpu().numpy(), counts.cpu().numpy(), int(overflow.item())
-    if ovf:
-        raise RuntimeError('scd_vote: a cluster has more distinct names than the 16384-slot table')
+    if ovf:                 # cannot happen with the spill tables VotePlan allocates; kept as a guard for raw-ABI callers
+        raise RuntimeError('scd_vote: a cluster exhausted the shared-memory name table and no spill buffer was given')
     out = {}
     for c in cluster_ids:
         ctr = Counter()

@@ -61,7 +61,7 @@ class K_Means(_K_Means):
         self.size_max = size_max
         self.n_flow_solves_ = 0          # iterations whose size bounds were active (diagnostic, not in the reference)
 
-    def _assign(self, X, centers, labels_out, inertia_acc):
+    def _assign(self, X, centers, labels_out, inertia_acc, estep=None):
         """``_labels_constrained`` (:226-274) for the rows of ``X``: labels into ``labels_out`` (int64, device),
         ``inertia_acc += sum_i D[i, label_i]**2`` (:271-272)."""
         lib = _lib.load()

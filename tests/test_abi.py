@@ -31,7 +31,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in scd_b200.h but not exported'
     assert sorted(_lib.SIGNATURES) == declared, 'ctypes signatures out of sync with the header'
-    assert lib.scd_version() == 100
+    assert lib.scd_version() == 200
 
 
 def test_workspace_sizes_are_sane_without_a_gpu():

@@ -206,6 +206,79 @@ def step_estep_prof():
             print(f'   {nm:28s} mean={col.mean():12.0f} min={col.min():12.0f} max={col.max():12.0f}')
 
 
+def _time(fn, reps=10, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def step_naming_scale():
+    """The scoring/top-k launch at the per-rank shapes of the 1/2/4/8-GPU runs (one GPU is enough to see how the
+    kernel behaves on a small row shard or a vocabulary shard)."""
+    import numpy as np
+    import torch
+    from scd_b200 import naming, _lib
+    d = 768
+    print('SCD_NAME_WAIT_HINT_NS =', os.environ.get('SCD_NAME_WAIT_HINT_NS', '(unset)'))
+    Xall = torch.randn(160000, d, device='cuda'); Xall = (Xall / Xall.norm(dim=1, keepdim=True)).bfloat16()
+    Wall = torch.randn(100000, d, device='cuda'); Wall = (Wall / Wall.norm(dim=1, keepdim=True)).bfloat16()
+    shapes = [(127000, 21000), (63500, 21000), (31750, 21000), (15875, 21000),           # C2 rows / N
+              (127000, 10500), (127000, 5250), (127000, 2625),                              # C2 vocabulary / N
+              (127000, 82000), (15875, 82000), (127000, 10250), (31750, 41000),             # C4: rows/8, vocab/8, 4x2 grid
+              (160000, 100000)]                                                             # C5 rows / 8
+    for n, v in shapes:
+        X, vocab = Xall[:n].contiguous(), naming.Vocabulary.from_rows(Wall[:v].contiguous())
+        plan = naming.TopKPlan(n, v, 5, 'cuda')
+        ms = _time(lambda: plan.run(X, vocab, False), reps=5 if n * v > 5e9 else 20)
+        pl = np.zeros(6, dtype=np.int32)
+        _lib.load().scd_name_topk_plan(n, v, 5, pl.ctypes.data)
+        print(f'rows {n:7d} x vocab {v:6d}: {ms*1e3:9.1f} us  {2*n*v*d/ms/1e9:7.1f} TFLOP/s   plan rb={pl[0]} tiles={pl[1]} full_rb={pl[2]} vsplit={pl[3]} tpc={pl[4]} pairs={pl[5]}')
+
+
+def step_small_kernels():
+    """The k-means pass and the vote at the row counts of a 1-GPU and an 8-GPU rank (everything but the big GEMM)."""
+    import torch
+    from scd_b200 import kmeans, naming
+    d, k = 768, 100
+    for n in (127000, 15875):
+        X = torch.randn(n, d, device='cuda'); X = X / X.norm(dim=1, keepdim=True)
+        C = X[:k].clone(); cn = torch.empty_like(C)
+        labels = torch.empty(n, dtype=torch.int64, device='cuda'); acc = torch.zeros(1, dtype=torch.float64, device='cuda')
+        ms_, es = kmeans._MStep(n, d, k, 'cuda'), kmeans._EStep(k, d, 'cuda')
+        print(f'--- rows {n}')
+        print(f'estep (+split)        {_time(lambda: kmeans._estep(X, C, labels, acc))*1e3:8.1f} us')
+        def estep_ready():
+            es.ready_for = C.data_ptr(); es.run(X, C, labels, acc)
+        es.run(X, C, labels, acc)
+        print(f'estep (planes ready)  {_time(estep_ready)*1e3:8.1f} us')
+        print(f'mstep sums            {_time(lambda: ms_.sums_counts(X, labels))*1e3:8.1f} us')
+        print(f'finalize (+planes)    {_time(lambda: ms_.finalize(C, cn, estep=es, shift=False))*1e3:8.1f} us')
+        print(f'finalize (+shift)     {_time(lambda: ms_.finalize(C, cn))*1e3:8.1f} us')
+    n = 127000
+    idx = torch.randint(0, 21000, (n, 5), device='cuda'); idx[:, 0] = torch.randint(0, 300, (n,), device='cuda')
+    labels = torch.randint(0, k, (n,), device='cuda')
+    vp = naming.VotePlan(n, k, 20, 'cuda')
+    ms_ = kmeans._MStep(n, d, k, 'cuda')
+    X = torch.randn(n, d, device='cuda')
+    ms_.sums_counts(X, labels)
+    print(f'vote (sort + vote)    {_time(lambda: naming.vote_device(idx, labels, k, 5, 20, plan=vp))*1e3:8.1f} us')
+    print(f'vote presorted        {_time(lambda: naming.vote_device(idx, None, k, 5, 20, plan=vp, presorted=ms_))*1e3:8.1f} us')
+    rec = naming.pack_vote_records(labels, idx, 5)
+    print(f'pack records          {_time(lambda: naming.pack_vote_records(labels, idx, 5, out=rec))*1e3:8.1f} us')
+    print(f'vote records          {_time(lambda: naming.vote_records(rec, k, 20, plan=vp))*1e3:8.1f} us')
+    n5, k5 = 1280000, 1000
+    idx = torch.randint(0, 100000, (n5, 5), device='cuda'); labels = torch.randint(0, k5, (n5,), device='cuda')
+    vp = naming.VotePlan(n5, k5, 20, 'cuda')
+    print(f'C5 vote (sort + vote) {_time(lambda: naming.vote_device(idx, labels, k5, 5, 20, plan=vp), reps=5)*1e3:8.1f} us')
+
+
 STEPS = ['kmeans', 'naming_tiny', 'naming_shapes', 'vote', 'naming_time']
 
 if __name__ == '__main__':
