@@ -378,8 +378,12 @@ class Round:
         self.cur = 0
         self.estep.ready_for = None
 
-    def capture(self):
-        """Record two rounds (centres C[0] -> C[1] and C[1] -> C[0]) into CUDA graphs: the round is launch-bound at N > 1."""
+    def capture(self, n_graphs=2):
+        """Record rounds into CUDA graphs (the round is launch-bound at N > 1).  Successive rounds alternate between the
+        two centre buffers, so graphs come in pairs: graphs[i] is the round that starts from C[i & 1].  Every graph
+        carries its own pair of EXTERNAL timing events around the scoring/top-k launches (event-record nodes), so the
+        dominant kernel is timed inside the replayed, back-to-back region itself - one sample per timed step."""
+        n_graphs = max(2, n_graphs + (n_graphs & 1))
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -389,13 +393,19 @@ class Round:
                 self.run(); self.run()                       # steady state: the operands of C[0] are in the E-step workspace
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            graphs = []
-            for _ in range(2):                               # graphs[i] is the round that starts from C[i]
+            graphs, events = [], []
+            pool = torch.cuda.graph_pool_handle()
+            for _ in range(n_graphs):
+                try:
+                    evs = (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+                except TypeError:
+                    evs = None
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):
-                    self.run()
+                with torch.cuda.graph(g, stream=side, pool=pool):
+                    self.run(ev_name=evs)
                 graphs.append(g)
-            self.graphs = graphs
+                events.append(evs)
+            self.graphs, self.graph_events, self.gstep = graphs, events, 0
         except Exception as e:                                  # eager launches are always available
             sys.stderr.write(f'[bench] CUDA graph capture failed, timing eager launches: {e}\n')
             self.graphs = None
@@ -404,11 +414,24 @@ class Round:
 
     def step(self):
         if self.graphs is not None:
-            self.graphs[self.cur].replay()
+            self.graphs[self.gstep % len(self.graphs)].replay()
+            self.gstep += 1
             self.cur ^= 1
             self.estep.ready_for = self.C[self.cur].data_ptr()
         else:
             self.run()
+
+    def graph_kernel_ms(self, last_n):
+        """Scoring/top-k durations (ms) recorded by the event nodes of the last `last_n` replays, or None."""
+        if self.graphs is None or not self.graph_events or self.graph_events[0] is None:
+            return None
+        n = len(self.graphs)
+        try:
+            idx = {(self.gstep - 1 - j) % n for j in range(min(last_n, n, self.gstep))}
+            return [self.graph_events[i][0].elapsed_time(self.graph_events[i][1]) for i in sorted(idx)]
+        except Exception as e:
+            sys.stderr.write(f'[bench] event nodes inside the graphs could not be read ({e}); timing eager launches instead\n')
+            return None
 
     def drop_graphs(self):
         self.graphs = None
@@ -426,7 +449,7 @@ def measure(rnd, steps, warmup, world, group, use_graph, sampler=None):
     for _ in range(warmup):
         rnd.run()
     barrier()
-    graphed = rnd.capture() if use_graph else False
+    graphed = rnd.capture(min(steps, 64)) if use_graph else False
     if world > 1:                                   # every rank must take the same path (collectives inside)
         import torch.distributed as dist
         flag = torch.tensor([1 if graphed else 0], device='cuda')
@@ -441,25 +464,37 @@ def measure(rnd, steps, warmup, world, group, use_graph, sampler=None):
     if sampler is not None:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    name_evs = []
     ev0.record()
     for _ in range(steps):
-        rnd.step()
+        if graphed:
+            rnd.step()
+        else:                                       # eager: the same events, recorded around the launches of every timed step
+            evs = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            rnd.run(ev_name=evs)
+            name_evs.append(evs)
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
-    # the dominant kernel, timed live with events around its launch (eager launches, same stream, same inputs)
-    n_k = max(3, min(steps, 20))
-    name_evs = []
-    for _ in range(n_k):
-        evs = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        rnd.run(ev_name=evs)
-        name_evs.append(evs)
-    barrier()
-    name_ms = float(np.mean([a.elapsed_time(b) for a, b in name_evs]))
+    # the dominant kernel, timed live INSIDE the timed region: event-record nodes of the replayed graphs (or the eager
+    # events above); only if a graph could not carry events, a few eager rounds right after the region
+    per_step = rnd.graph_kernel_ms(steps) if graphed else [a.elapsed_time(b) for a, b in name_evs]
+    where = 'event nodes inside the replayed graphs' if graphed else 'events around the eager launches of the timed steps'
+    if per_step is None:
+        name_evs = []
+        for _ in range(max(3, min(steps, 20))):
+            evs = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            rnd.run(ev_name=evs)
+            name_evs.append(evs)
+        barrier()
+        per_step = [a.elapsed_time(b) for a, b in name_evs]
+        where = 'eager rounds right after the timed region'
+    name_ms = float(np.mean(per_step))
     t = torch.tensor([ms_total, name_ms], dtype=torch.float64, device='cuda')
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    rnd.kernel_timing = f'{where}, mean of {len(per_step)} steps'
     return float(t[0]) / steps, float(t[1]), graphed
 
 
@@ -652,12 +687,12 @@ def main():
     roofline = dict(bound='tensor', kernel='name_topk_kernel<5> (+ topk_merge)', achieved=round(achieved, 1), peak=peaks['tflops'],
                     unit='TFLOP/s', frac=round(achieved / peaks['tflops'], 4), traffic=traffic,
                     peak_source=f"{peaks['source']} bf16 burst (MEASURED_PEAKS.json); sustained figure: {peaks['tflops_sustained']}",
-                    kernel_ms=round(name_ms, 4), flops_per_launch=flops)
+                    kernel_ms=round(name_ms, 4), flops_per_launch=flops, kernel_timing=rnd.kernel_timing)
 
     # sustained regime: the same graph replayed back to back for >= 2 s (power-capped clocks), against the sustained peak
     sustained = None
     if not args.no_extra and world == 1:
-        rnd.capture()
+        rnd.capture(2)
         n_rep = max(50, int(2200.0 / max(ms_per_step, 0.05)))
         s2 = ClockSampler(physical_gpu_index(local_rank), enabled=not args.no_clocks)
         torch.cuda.synchronize()
@@ -670,11 +705,15 @@ def main():
         torch.cuda.synchronize()
         ms_sus = e0.elapsed_time(e1) / n_rep
         ck = s2.result()
-        est_name = ms_sus - (ms_per_step - name_ms)
-        sustained = dict(rounds=n_rep, seconds=round(ms_sus * n_rep / 1e3, 2), ms_per_step=round(ms_sus, 4),
-                         est_kernel_tflops=round(flops / (est_name * 1e-3) / 1e12, 1),
-                         est_kernel_frac_of_sustained_peak=round(flops / (est_name * 1e-3) / 1e12 / peaks['tflops_sustained'], 4),
-                         note='kernel time estimated as the sustained round minus the burst-measured rest of the round', clocks=ck)
+        k_ms = rnd.graph_kernel_ms(2)
+        if k_ms:
+            k_sus, how = float(np.mean(k_ms)), 'event nodes of the last two replays'
+        else:
+            k_sus, how = ms_sus - (ms_per_step - name_ms), 'sustained round minus the burst-measured rest of the round'
+        sustained = dict(rounds=n_rep, seconds=round(ms_sus * n_rep / 1e3, 2), ms_per_step=round(ms_sus, 4), kernel_ms=round(k_sus, 4),
+                         kernel_tflops=round(flops / (k_sus * 1e-3) / 1e12, 1),
+                         kernel_frac_of_sustained_peak=round(flops / (k_sus * 1e-3) / 1e12 / peaks['tflops_sustained'], 4),
+                         kernel_timing=how, clocks=ck)
         rnd.drop_graphs()
 
     e2e = None

@@ -151,18 +151,27 @@ def naming_loop_unsup(name_idx_topk: torch.Tensor, u_preds: np.ndarray, clip_u_f
 
 def naming_loop_ptsup(name_idx_topk: torch.Tensor, all_preds: np.ndarray, mask_lab: np.ndarray,
                       clip_u_feats, zeroshot_weights: torch.Tensor, lab_name_idx, n_cluster: int,
-                      top_k=5, num_common_vote=20, num_common_linear=4, max_rounds=50):
-    """main_ptsup.py:588-676 with names as vocabulary indices (so ``sorted(cand_names)`` :659 sorts
-    integers here - the fixtures use index-named vocabularies on both sides).
+                      top_k=5, num_common_vote=20, num_common_linear=4, max_rounds=50, nouns=None):
+    """main_ptsup.py:588-676.  ``nouns=None``: names are vocabulary indices (``sorted(cand_names)`` :659 sorts
+    integers - the committed fixtures use index-named vocabularies on both sides).  ``nouns`` = the vocabulary's
+    name strings: the loop works on strings exactly as the reference does - ``sorted`` is lexicographic,
+    ``nouns.index`` resolves duplicates to the first occurrence (:601, :669), the convergence test compares name sets,
+    and ``list(set(cand_names) - set(lab_names))`` (:664) takes CPython's string-set order of the running process.
 
     Reproduces the reference's index-space quirk: from round 2 on ``unlab_cluster_idx`` and
     ``known_name_idx`` are positions in ``cand_names`` (:662-666) while ``name_idx_topk`` still holds
     vocabulary indices."""
     u_preds = all_preds[~mask_lab]                                                 # ref :592
     l_preds = all_preds[mask_lab]                                                  # ref :593
-    lab_names = list(lab_name_idx)                                                 # ref :598
+    name_of = (lambda i: i) if nouns is None else (lambda i: nouns[i])
+    first = None if nouns is None else {}
+    if nouns is not None:
+        for i, s in enumerate(nouns):
+            first.setdefault(s, i)
+    index_of = (lambda s: s) if nouns is None else (lambda s: first[s])            # nouns.index(s)
+    lab_names = [name_of(int(i)) for i in lab_name_idx]                            # ref :598
     num_unlab = n_cluster - len(lab_names)                                         # ref :602
-    known = list(lab_names)                                                        # ref :603 (index in nouns)
+    known = [index_of(s) for s in lab_names]                                       # ref :603 (index in nouns)
     unlab_clusters = list(set(set(all_preds)) - set(l_preds))                      # ref :625
     cur, prev = [-1], [-2]
     trace = []
@@ -171,12 +180,13 @@ def naming_loop_ptsup(name_idx_topk: torch.Tensor, all_preds: np.ndarray, mask_l
         uniq = voted_candidates(c2c, unlab_clusters, num_common_vote)                     # ref :640-648
         ind, w = assign_name(uniq, c2c, num_common=num_common_linear)                     # ref :649
         prev = copy.deepcopy(cur)
-        cur = [int(uniq[x[1]]) for x in ind[:num_unlab]]                                  # ref :655
+        cur = [name_of(int(uniq[x[1]])) for x in ind[:num_unlab]]                         # ref :655
         cand = sorted(set(cur + lab_names))                                               # ref :657-659
         lab_class_index = [cand.index(n) for n in lab_names]                              # ref :662
         unlab_clusters = [cand.index(n) for n in list(set(cand) - set(lab_names))]        # ref :664
         known = copy.deepcopy(lab_class_index)                                            # ref :666
-        w_sel = torch.stack([zeroshot_weights[:, n] for n in cand], dim=1)                # ref :668-669
+        cand_idx = [index_of(s) for s in cand]
+        w_sel = torch.stack([zeroshot_weights[:, n] for n in cand_idx], dim=1)            # ref :668-669
         u_preds = reassign(clip_u_feats, w_sel)                                           # ref :671-676
         trace.append(dict(voted=list(cur), cand=list(cand), u_preds=u_preds.copy(), n_unique=len(uniq)))
     return trace

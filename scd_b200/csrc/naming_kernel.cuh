@@ -103,7 +103,6 @@ struct NameParams {
   long long* prof;         // nullable: [pairs][16] cycle counters (scd_debug_set_name_profile), debugging aid
   const __nv_bfloat16* x;  // [N, d] row-major: the loader warps read the TMEM-resident k-blocks straight from global memory
   int d;
-  unsigned wait_hint_ns;   // 0: plain try_wait spin; > 0: suspend-time hint of the long waits (producers, loaders, epilogue)
 };
 
 // One sorted top-KT list in registers, ordered by (value descending, column ascending) - the order
@@ -256,7 +255,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           const int stage = (int)(g % kBStages);
           const uint32_t phase = (g / kBStages) & 1u;
           { const long long c0 = prof ? clock64() : 0;
-            ptx::mbar_wait_hint(empty_bar(stage), phase ^ 1, 200 + stage, p.wait_hint_ns);
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1, 200 + stage);
             if (prof) pf_e += clock64() - c0; }
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * kBStageBytes);
@@ -290,7 +289,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           if (row < p.n_rows && kb * kAKBlock + q * 8 < p.d) v = __ldg(src + kb * 8 + q);
           r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
         }
-        ptx::mbar_wait_hint(a_empty_bar(kb), (my_item_no & 1) ^ 1, 150 + kb, p.wait_hint_ns);
+        ptx::mbar_wait(a_empty_bar(kb), (my_item_no & 1) ^ 1, 150 + kb);
         ptx::tc_fence_after_sync();
         ptx::tmem_st_32x32(tmem_base + lane_addr + a_tmem_col(kb, 0), r);
         ptx::tmem_st_wait();
@@ -303,7 +302,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       if (warp == 12) {
         const int row0 = item_rb(it) * 2 * kBlockM + (int)cta_rank * kBlockM;
         for (int kb = kTmemAKBlocks; kb < nkb; ++kb) {
-          ptx::mbar_wait_hint(a_empty_bar(kb), (my_item_no & 1) ^ 1, 100 + kb, p.wait_hint_ns);
+          ptx::mbar_wait(a_empty_bar(kb), (my_item_no & 1) ^ 1, 100 + kb);
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_arrive_expect_tx(a_full_bar(kb), 2 * kABlockBytes);
             ptx::tma_load_2d<2>(sbase + NameSmem::a_off + (kb - kTmemAKBlocks) * kABlockBytes, &map_x,
@@ -311,6 +310,8 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           }
           __syncwarp();
         }
+        if (p.prof != nullptr && pair == 0 && leader && lane == 0 && my_item_no < 64)
+          p.prof[(size_t)n_pairs * 32 + 4 * 384 + my_item_no * 6 + 5] = clock64();                // the item's rows are on their way
       }
     }
   } else if (warp == 1 || warp == 3 || warp == 16) {
@@ -383,6 +384,8 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               ptx::tc_fence_after_sync();
             }
             const long long tr1 = trace ? clock64() : 0;
+            if (p.prof != nullptr && pair == 0 && t == 0 && kb == 0 && lane == 0 && my_item_no < 64)
+              p.prof[(size_t)n_pairs * 32 + 4 * 384 + my_item_no * 6 + 0] = clock64();            // first k-block of the item issued
             const bool elected = ptx::elect_one();
             if (elected) {
               if (a_in_tmem) {
@@ -430,9 +433,11 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     long long pf_t0 = prof ? clock64() : 0, pf_w = 0, pf_fin = 0;
     long long* const trace = (prof && pair == 0) ? p.prof + (size_t)n_pairs * 32 + 2 * 384 : nullptr;
     int n_ev = 0;
-    for (int it = pair; it < n_items; it += n_pairs) {
+    int epi_item_no = 0;
+    for (int it = pair; it < n_items; it += n_pairs, ++epi_item_no) {
       const int nt = item_ntiles(it);
       const long long row = (long long)item_rb(it) * 2 * kBlockM + cta_rank * kBlockM + quad * 32 + lane;
+      long long* const itrace = (prof && pair == 0 && lane == 0 && epi_item_no < 64) ? p.prof + (size_t)n_pairs * 32 + 4 * 384 + epi_item_no * 6 : nullptr;
       ctop.reset();
       float run_max = -INFINITY, run_sum = 0.f;
 
@@ -472,9 +477,10 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         const int half_cols = half == 0 ? kHalfCols : kTileN - kHalfCols;
         const int n_valid = (int)min((long long)half_cols, p.v_total - col0);      // may be <= 0 on the last tile
         { const long long c0 = prof ? clock64() : 0;
-          ptx::mbar_wait_hint(tmem_full_bar(buf), (tile_no >> 1) & 1u, 600 + buf, p.wait_hint_ns);
+          ptx::mbar_wait(tmem_full_bar(buf), (tile_no >> 1) & 1u, 600 + buf);
           if (prof) pf_w += clock64() - c0; }
         ptx::tc_fence_after_sync();
+        if (itrace && t == 0) itrace[1] = clock64();                                            // first tile of the item seen
         const long long tr0 = trace ? clock64() : 0;
         const uint32_t taddr = tmem_base + lane_addr + buf * kAccStride + half * kHalfCols;
         // four 32-column chunks in the first half, three in the second (96 columns).  Its fourth chunk would be the
@@ -513,6 +519,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       // local memory: divergent st.local, ~28 k cycles per item with the tensor pipe idle for ~18 k of them - 4 % of a
       // whole-vocabulary sweep but 20-37 % of the short items a small row shard is cut into)
       const long long pf_c1 = prof ? clock64() : 0;
+      if (itrace) itrace[2] = pf_c1;                                                            // last tile processed
       TopK<KT> top;
       top.reset();
       {
@@ -579,6 +586,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           }
         }
       }
+      if (itrace) itrace[3] = clock64();                                                        // exact scan done
       if (row < p.n_rows) {
         const long long slot = (long long)(item_chunk(it) * kEpiHalves + (int)half) * p.n_rows + row;
 #pragma unroll
@@ -587,6 +595,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         p.part_sum[slot] = run_sum;
       }
       if (prof) pf_fin += clock64() - pf_c1;
+      if (itrace) itrace[4] = clock64();
     }
     if (prof && lane == 0) {
       long long* o = p.prof + (size_t)pair * 32;

@@ -168,30 +168,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   }
 }
 
-// try_wait with an explicit suspend-time hint: the thread may sleep in hardware for up to `hint_ns` and is woken when
-// the phase completes.  For waits that are expected to be long (a whole tile or a whole work item): a plain try_wait
-// loop returns every ~40 cycles and the spinning warps (two thirds of all instructions the naming kernel executed in
-// round 1, profiles/r1s_*) cost issue slots and power on a part whose tensor clock is power-limited.
-__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(hint_ns)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity, int tag, uint32_t hint_ns) {
-  if (hint_ns == 0u) { mbar_wait(bar, parity, tag); return; }
-  if (mbar_try_wait(bar, parity)) return;
-  WaitClock clk;
-  while (!mbar_try_wait_hint(bar, parity, hint_ns)) {
-    if (clk.expired()) mbar_timeout_trap(bar, parity, tag);
-  }
-}
-
 __device__ __forceinline__ void mbar_wait2(uint32_t bar0, uint32_t bar1, uint32_t parity, int tag = 0) {
   if (mbar_try_wait2(bar0, bar1, parity)) return;
   WaitClock clk;

@@ -173,16 +173,6 @@ bool plan_naming(int64_t N, int64_t V, int k, NamePlan* pl) {
   return true;
 }
 
-// suspend-time hint (ns) of the naming kernel's long mbarrier waits; SCD_NAME_WAIT_HINT_NS overrides (0 = plain spin)
-unsigned name_wait_hint_ns() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = std::getenv("SCD_NAME_WAIT_HINT_NS");
-    cached = e ? std::max(0, std::atoi(e)) : 0;
-  }
-  return (unsigned)cached;
-}
-
 template <int KT>
 int launch_name_topk(const CUtensorMap& mx, const CUtensorMap& mw, const scd::NameParams& p, int n_pairs, cudaStream_t st) {
   static bool attr_set[kMaxDevices] = {};
@@ -578,7 +568,6 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
   p.prof = g_name_prof;
   p.x = reinterpret_cast<const __nv_bfloat16*>(X);
   p.d = D;
-  p.wait_hint_ns = name_wait_hint_ns();
   if (pl.n_vsplit > 1) SCD_CUDA(cudaMemsetAsync(p.part_idx, 0xFF, pl.idx_bytes, st));   // -1: "row has nothing in this part"
 
   int e = 0;

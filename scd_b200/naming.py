@@ -404,16 +404,31 @@ def naming_loop_unsup(name_idx_topk, u_preds, clip_u_feats, zeroshot_weights, n_
 
 
 def naming_loop_ptsup(name_idx_topk, all_preds, mask_lab, clip_u_feats, zeroshot_weights, lab_name_idx, n_cluster,
-                      top_k=5, num_common_vote=20, num_common_linear=4, max_rounds=50):
+                      top_k=5, num_common_vote=20, num_common_linear=4, max_rounds=50, nouns=None):
     """``main_ptsup.py:588-676`` including its index-space quirk (from round 2 ``unlab_cluster_idx`` /
-    ``known_name_idx`` are positions in ``cand_names`` while ``name_idx_topk`` holds vocabulary indices)."""
+    ``known_name_idx`` are positions in ``cand_names`` while ``name_idx_topk`` holds vocabulary indices).
+
+    ``nouns`` (optional, the vocabulary's name strings in column order): the bookkeeping then runs on the strings like
+    the reference - ``sorted(cand_names)`` :659 is lexicographic (it fixes ``lab_class_index``, the numbering of the
+    re-assigned clusters and the row order of the Hungarian matrix), ``nouns.index`` :601 / :669 maps duplicate names
+    to their first column, the loop ends when the SET OF NAMES stops changing, and :664's
+    ``list(set(cand_names) - set(lab_names))`` takes the string-set order of the running interpreter (hash-seed
+    dependent in the reference too).  Without ``nouns`` a name is its column index - equivalent whenever the
+    vocabulary list is duplicate-free and in lexicographic order.  ``voted`` / ``cand`` in the trace are names."""
     vocab = _as_vocab(zeroshot_weights)
     feats = _feats_bf16(clip_u_feats)
     all_preds, mask_lab = np.asarray(all_preds), np.asarray(mask_lab)
     u_preds, l_preds = all_preds[~mask_lab], all_preds[mask_lab]                    # :592-593
-    lab_names = list(lab_name_idx)
+    if nouns is None:
+        name_of, index_of = (lambda i: i), (lambda s: s)
+    else:
+        first = {}
+        for i, s in enumerate(nouns):
+            first.setdefault(s, i)
+        name_of, index_of = (lambda i: nouns[i]), (lambda s: first[s])              # nouns.index(s)
+    lab_names = [name_of(int(i)) for i in lab_name_idx]                             # :598
     num_unlab = n_cluster - len(lab_names)                                          # :602
-    known = list(lab_names)                                                         # :603
+    known = [index_of(s) for s in lab_names]                                        # :603
     unlab_clusters = list(set(set(all_preds)) - set(l_preds))                       # :625
     cur, prev, trace = [-1], [-2], []
     while set(cur) != set(prev) and len(trace) < max_rounds:
@@ -421,11 +436,11 @@ def naming_loop_ptsup(name_idx_topk, all_preds, mask_lab, clip_u_feats, zeroshot
         uniq = voted_candidates(c2c, unlab_clusters, num_common_vote)               # :640-648
         ind, _w = assign_name(uniq, c2c, num_common=num_common_linear)              # :649
         prev = copy.deepcopy(cur)
-        cur = [int(uniq[x[1]]) for x in ind[:num_unlab]]                            # :655
+        cur = [name_of(int(uniq[x[1]])) for x in ind[:num_unlab]]                   # :655
         cand = sorted(set(cur + lab_names))                                         # :657-659
         lab_class_index = [cand.index(n) for n in lab_names]                        # :662
         unlab_clusters = [cand.index(n) for n in list(set(cand) - set(lab_names))]  # :664
         known = copy.deepcopy(lab_class_index)                                      # :666
-        u_preds = reassign(feats, vocab, cand)                                      # :668-676
+        u_preds = reassign(feats, vocab, [index_of(s) for s in cand])               # :668-676
         trace.append(dict(voted=list(cur), cand=list(cand), u_preds=u_preds.copy(), n_unique=len(uniq)))
     return trace

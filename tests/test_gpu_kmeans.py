@@ -270,12 +270,20 @@ def test_kpp_update_tracks_the_running_min_distance():
     want = None
     for step, idx in enumerate([5, 2999, 1234]):
         pick = torch.tensor([idx], dtype=torch.int64, device='cuda')
-        _lib.check(lib.scd_kpp_update(Xd.data_ptr(), n, d, pick.data_ptr(), int(step == 0), d2.data_ptr(), centre.data_ptr(),
+        _lib.check(lib.scd_kpp_update(Xd.data_ptr(), n, d, pick.data_ptr(), None, int(step == 0), d2.data_ptr(), centre.data_ptr(),
                                       ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), 'scd_kpp_update')
         dist = kmeans_oracle.pairwise_distance(X, X[idx:idx + 1], None).view(-1)
         want = dist if want is None else torch.minimum(want, dist)
         assert (d2.cpu() - want).abs().max() < 1e-5
         assert torch.equal(centre.cpu(), X[idx])
+        # the row-sharded form (the picked row arrives as a vector from another rank) gives the same update
+        d2b = d2.clone() if step else torch.empty_like(d2)
+        if step:
+            d2b.copy_(prev)
+        _lib.check(lib.scd_kpp_update(Xd.data_ptr(), n, d, None, Xd[idx].contiguous().data_ptr(), int(step == 0), d2b.data_ptr(), None,
+                                      ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), 'scd_kpp_update')
+        assert torch.equal(d2b, d2)
+        prev = d2.clone()
         sums = ws[:((n + 63) // 64) * 8].view(torch.float64).cpu()
         assert abs(float(sums.sum()) - float(d2.double().sum())) < 1e-9 * max(1.0, float(sums.sum()))
 

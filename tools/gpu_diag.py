@@ -146,7 +146,7 @@ def step_name_prof():
     vocab = naming.Vocabulary.from_rows(W)
     for _ in range(2):
         naming.name_topk_raw(X, vocab, 5, False)
-    prof = torch.zeros(74 * 32 + 4 * 384, dtype=torch.int64, device='cuda')
+    prof = torch.zeros(74 * 32 + 5 * 384, dtype=torch.int64, device='cuda')
     _lib.load().scd_debug_set_name_profile(prof.data_ptr())
     naming.name_topk_raw(X, vocab, 5, False)
     torch.cuda.synchronize()
@@ -277,6 +277,45 @@ def step_small_kernels():
     idx = torch.randint(0, 100000, (n5, 5), device='cuda'); labels = torch.randint(0, k5, (n5,), device='cuda')
     vp = naming.VotePlan(n5, k5, 20, 'cuda')
     print(f'C5 vote (sort + vote) {_time(lambda: naming.vote_device(idx, labels, k5, 5, 20, plan=vp), reps=5)*1e3:8.1f} us')
+
+
+def step_name_items():
+    """Per-work-item timeline of the naming kernel (pair 0) at a full-size and two small-shard shapes: where does the
+    fixed cost per work item go?"""
+    import numpy as np
+    import torch
+    from scd_b200 import naming, _lib
+    d = 768
+    Xall = torch.randn(127000, d, device='cuda'); Xall = (Xall / Xall.norm(dim=1, keepdim=True)).bfloat16()
+    Wall = torch.randn(21000, d, device='cuda'); Wall = (Wall / Wall.norm(dim=1, keepdim=True)).bfloat16()
+    for n, v in ((127000, 21000), (15875, 21000), (127000, 2625)):
+        X, vocab = Xall[:n].contiguous(), naming.Vocabulary.from_rows(Wall[:v].contiguous())
+        plan = naming.TopKPlan(n, v, 5, 'cuda')
+        for _ in range(2):
+            plan.run(X, vocab, False)
+        ms = _time(lambda: plan.run(X, vocab, False), reps=5)
+        prof = torch.zeros(74 * 32 + 5 * 384, dtype=torch.int64, device='cuda')
+        _lib.load().scd_debug_set_name_profile(prof.data_ptr())
+        plan.run(X, vocab, False)
+        torch.cuda.synchronize()
+        _lib.load().scd_debug_set_name_profile(None)
+        full = prof.cpu()
+        p = full[:74 * 32].view(74, 32).double()
+        pl = np.zeros(6, dtype=np.int32)
+        _lib.load().scd_name_topk_plan(n, v, 5, pl.ctypes.data)
+        print(f'=== rows {n} x vocab {v}: {ms*1e3:.1f} us; plan rb={pl[0]} tiles={pl[1]} full_rb={pl[2]} vsplit={pl[3]} tpc={pl[4]}')
+        for k, nm in {0: 'issuer total', 1: 'issuer wait tmem_empty', 2: 'issuer wait a_full', 3: 'issuer wait b_full', 4: 'issuer wait token',
+                      5: 'tiles', 8: 'epi total', 9: 'epi wait tmem_full', 10: 'epi item-final scan+write'}.items():
+            col = p[:, k]
+            print(f'   {nm:28s} mean={col.mean():11.0f} min={col.min():11.0f} max={col.max():11.0f}')
+        it = full[74 * 32 + 4 * 384:].view(64, 6)
+        t0 = int(it[0, 0]) if int(it[0, 0]) else int(it[0, 1])
+        print('   pair 0 items: first MMA | first tile seen | tiles done | scan done | results written | A loads issued   (cycles since the first MMA)')
+        for i in range(64):
+            if int(it[i, 1]) == 0:
+                break
+            a = [int(x) - t0 if int(x) else -1 for x in it[i].tolist()]
+            print(f'     item {i:2d}: {a[0]:9d} {a[1]:9d} {a[2]:9d} {a[3]:9d} {a[4]:9d} {a[5]:9d}   (tiles {a[2]-a[1]:8d}, scan {a[3]-a[2]:6d}, write {a[4]-a[3]:6d})')
 
 
 STEPS = ['kmeans', 'naming_tiny', 'naming_shapes', 'vote', 'naming_time']
