@@ -39,10 +39,11 @@ def all_gather_into(out: torch.Tensor, inp: torch.Tensor, group=None):
     """``dist.all_gather_into_tensor`` (NCCL on the GPUs).  gloo has no all-gather for CUDA tensors - the multi-rank
     tests that share one GPU stage through the host there."""
     import torch.distributed as dist
-    if inp.is_cuda and dist.get_backend(group) == 'gloo':
-        host = torch.empty(out.shape, dtype=out.dtype)
-        dist.all_gather_into_tensor(host, inp.cpu().contiguous(), group=group)
-        out.copy_(host)
+    if dist.get_backend(group) == 'gloo':
+        # gloo chunks the output along dim 0 and wants every chunk shaped like the input: exchange flat buffers
+        host = torch.empty(out.numel(), dtype=out.dtype)
+        dist.all_gather_into_tensor(host, inp.detach().cpu().contiguous().view(-1), group=group)
+        out.copy_(host.view(out.shape))
         return out
     dist.all_gather_into_tensor(out, inp, group=group)
     return out
