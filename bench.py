@@ -281,7 +281,7 @@ class Round:
     Successive rounds are successive k-means iterations: the centres ping-pong between two buffers and
     scd_finalize_centers leaves the next E-step's operands in place, exactly like K_Means._lloyd."""
 
-    def __init__(self, cfg, rank, world, group, naming_shard='rows', vocab_ways=None, data=None, host_data=None):
+    def __init__(self, cfg, rank, world, group, naming_shard='rows', vocab_ways=None, data=None, host_data=None, exchange='peer'):
         from scd_b200 import dist as sdist, kmeans, naming, synth
         self.cfg, self.rank, self.world, self.group = cfg, rank, world, group
         self.kmeans, self.naming, self.sdist = kmeans, naming, sdist
@@ -303,7 +303,14 @@ class Round:
         self.estep = kmeans._EStep(cfg.k, d, dev)
         self.km = kmeans.K_Means(k=cfg.k, process_group=group if world > 1 else None)
         self.labels = torch.empty(n_local, dtype=torch.int64, device=dev)
-        self.g_rec = sdist.RowGather(cfg.n, (1 + TOPK,), torch.int32, dev, group) if world > 1 else None
+        # the two exchange steps: NVLink peer memory (the fused kernels of scd_b200/peer.py) unless --exchange nccl
+        self.px = None
+        if world > 1 and exchange == 'peer':
+            from scd_b200 import peer
+            self.px = peer.PeerExchange(group, cfg.k, d, n_total=cfg.n, k_used=TOPK, device=dev)
+            self.inertia_red = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.g_rec = sdist.RowGather(cfg.n, (1 + TOPK,), torch.int32, dev, group) if world > 1 and self.px is None else None
+        self.records = None
         self.subgroup = None
         if self.naming_shard == 'rows':
             self.name_rows = (self.row_lo, self.row_hi)
@@ -344,13 +351,20 @@ class Round:
         launches = 0
         c_old, c_new = self.C[self.cur], self.C[self.cur ^ 1]
         # ---- k-means iteration: E-step, M-step sums, (all-reduce), divide (+ next E-step's operands)
-        self.inertia.zero_()
+        inertia = self.inertia
+        if self.px is not None:                     # this round's [sums | counts | inertia] block, mapped by every rank
+            self.mstep.bind_peer(self.px, self.px.next_mstep_block())
+            inertia = self.mstep.peer[1][2]
+        inertia.zero_()
         ready = self.estep.ready_for == c_old.data_ptr()
-        self.estep.run(self.X, c_old, self.labels, self.inertia); launches += 1 if ready else 2     # (centroid split +) E-step
+        self.estep.run(self.X, c_old, self.labels, inertia); launches += 1 if ready else 2     # (centroid split +) E-step
         self.mstep.sums_counts(self.X, self.labels); launches += 3                    # hist+scan, scatter, segment sum
-        counts_f = self.km._allreduce(self.mstep, self.inertia)
-        launches += 1 if counts_f is not None else 0                                  # pack (the all-reduce is NCCL's)
-        self.mstep.finalize(c_old, c_new, counts_f, estep=self.estep, shift=False); launches += 1
+        if self.px is not None:                     # all-reduce over peer loads + divide + next E-step operands: one launch
+            self.mstep.finalize_peer(c_old, c_new, self.inertia_red, estep=self.estep); launches += 1
+        else:
+            counts_f = self.km._allreduce(self.mstep, self.inertia)
+            launches += 1 if counts_f is not None else 0                              # pack (the all-reduce is NCCL's)
+            self.mstep.finalize(c_old, c_new, counts_f, estep=self.estep, shift=False); launches += 1
         # ---- full-vocabulary scoring + per-image top-5
         if ev_name is not None:
             ev_name[0].record()
@@ -366,7 +380,9 @@ class Round:
         if self.world == 1:
             out = nm.vote_device(idx, None, cfg.k, TOPK, NUM_COMMON, plan=self.vote_plan, presorted=self.mstep); launches += 1
         else:
-            out = self.sdist.sharded_vote(self.labels, idx, TOPK, cfg.k, NUM_COMMON, self.g_rec, plan=self.vote_plan); launches += 4
+            gat = self.px if self.px is not None else self.g_rec
+            out = self.sdist.sharded_vote(self.labels, idx, TOPK, cfg.k, NUM_COMMON, gat, plan=self.vote_plan); launches += 5 if self.px is not None else 4
+            self.records = self.px._records[self.px._rec_parity ^ 1][0][:cfg.n] if self.px is not None else self.g_rec.full
         self.cur ^= 1
         self.launches_per_round = launches
         self.last = (vals, idx, out)
@@ -509,7 +525,7 @@ def parity_block(rnd, data, world, group):
     vals, idx, _ = rnd.last
     torch.cuda.synchronize()
     if world > 1:
-        rec = rnd.g_rec.full                                     # gathered [N, 1 + k] records of this very round
+        rec = rnd.records                                        # gathered [N, 1 + k] records of this very round
         labels_all, idx_all = rec[:, 0].long(), rec[:, 1:].long()
     else:
         labels_all, idx_all = rnd.labels, idx
@@ -533,13 +549,13 @@ def parity_block(rnd, data, world, group):
     return out
 
 
-def extra_block(name, rank, world, group, peaks, steps, naming_shard, vocab_ways=None):
+def extra_block(name, rank, world, group, peaks, steps, naming_shard, vocab_ways=None, exchange='peer'):
     """Timing + parity of one of the other BASELINE.json configs on the same N GPUs (device-generated inputs)."""
     from scd_b200 import synth
     cfg = synth.CONFIGS[name]
     t0 = time.time()
     data = device_data(cfg, torch.device('cuda'), synth.D)
-    rnd = Round(cfg, rank, world, group, naming_shard, vocab_ways, data=data)
+    rnd = Round(cfg, rank, world, group, naming_shard, vocab_ways, data=data, exchange=exchange)
     if world == 1:
         data_keep = None
     else:
@@ -602,6 +618,9 @@ def main():
     ap.add_argument('--naming-shard', default='rows', choices=['rows', 'vocab'],
                     help='N > 1: how the scoring/top-k is partitioned (rows: no exchange; vocab: all-gather + k-way merge)')
     ap.add_argument('--vocab-ways', type=int, default=0, help='with --naming-shard vocab: vocabulary shards per row group (default: N)')
+    ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl'],
+                    help='N > 1: the M-step sum and the vote-record replication run over NVLink peer memory inside the kernels '
+                         '(scd_b200/peer.py), or as NCCL all-reduce / all-gather launches between them')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of CUDA-graph replays')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-torch-baseline', action='store_true')
@@ -622,8 +641,13 @@ def main():
     if world == 1:
         par = 'single GPU'
     elif args.naming_shard == 'rows':
-        par = (f'rows/{world} for k-means (packed NCCL all-reduce of sums+counts+inertia) and for naming (vocabulary replicated, '
-               f'no exchange); [label, top-k names] int32 records all-gathered once, exact vote replicated')
+        if args.exchange == 'peer':
+            par = (f'rows/{world} for k-means (sums+counts+inertia summed over NVLink peer loads inside the divide kernel) and for '
+                   f'naming (vocabulary replicated, no exchange); [label, top-k names] int32 records stored into every rank over '
+                   f'peer memory by the pack kernel, exact vote replicated')
+        else:
+            par = (f'rows/{world} for k-means (packed NCCL all-reduce of sums+counts+inertia) and for naming (vocabulary replicated, '
+                   f'no exchange); [label, top-k names] int32 records all-gathered once, exact vote replicated')
     else:
         ways = args.vocab_ways or world
         par = (f'rows/{world} (k-means, all-reduce) x naming on a {world // ways} x {ways} rows x vocabulary grid (all-gather of '
@@ -667,7 +691,7 @@ def main():
         group = dist.group.WORLD
     peaks = load_peaks()
     host = synth.make(cfg)
-    rnd = Round(cfg, rank, world, group, args.naming_shard, args.vocab_ways or None, host_data=host)
+    rnd = Round(cfg, rank, world, group, args.naming_shard, args.vocab_ways or None, host_data=host, exchange=args.exchange)
 
     sampler = ClockSampler(physical_gpu_index(local_rank), enabled=not args.no_clocks)
     ms_per_step, name_ms, graphed = measure(rnd, args.steps, args.warmup, world, group, not args.no_graph, sampler)
@@ -755,11 +779,11 @@ def main():
     torch.cuda.empty_cache()
     if not args.no_extra:
         try:
-            extra['c5'] = extra_block('C5', rank, world, group, peaks, args.extra_steps, 'rows')
-            extra['c4_vocab_shard'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'vocab')
-            extra['c4_rows'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'rows')
+            extra['c5'] = extra_block('C5', rank, world, group, peaks, args.extra_steps, 'rows', exchange=args.exchange)
+            extra['c4_vocab_shard'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'vocab', exchange=args.exchange)
+            extra['c4_rows'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'rows', exchange=args.exchange)
             if world >= 4:
-                extra['c4_grid_2d'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'vocab', vocab_ways=2)
+                extra['c4_grid_2d'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'vocab', vocab_ways=2, exchange=args.exchange)
         except Exception as e:
             if world > 1:
                 raise                                              # a rank that skips a collective would hang the others

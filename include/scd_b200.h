@@ -127,10 +127,14 @@ SCD_API int scd_gather_rows_bf16(const scd_bf16_t* Wt, const int64_t* sel, int n
  * The N x V score matrix is never written. */
 SCD_API size_t scd_name_topk_workspace_bytes(int64_t N, int64_t V, int k);
 /* Introspection (no reference counterpart): the work partition scd_name_topk uses for (N, V, k) on the current device -
- * out[0] = 256-row blocks, out[1] = vocabulary tiles per sweep, out[2] = row blocks that sweep the whole vocabulary as
- * one work item (whole waves), out[3] = vocabulary chunks the remaining (tail-wave) row blocks are split into,
- * out[4] = tiles per chunk, out[5] = CTA pairs launched.  Host-only. */
+ * out[0] = 256-row blocks, out[1] = vocabulary tiles per sweep, out[2] = CTA pairs launched, out[3] = most pieces any
+ * row block is cut into (the (row block, tile) space is cut into one contiguous range per pair), out[4] = tiles of the
+ * least loaded pair (the busiest has at most one more), out[5] = work items the busiest pair starts.  Host-only. */
 SCD_API int scd_name_topk_plan(int64_t N, int64_t V, int k, int32_t* out6 /* host */);
+/* The work items of one CTA pair under that partition, in execution order: out[i] = {row block, first tile, tiles,
+ * piece ordinal of the row block (= partial-list slot)}.  Returns the number of items (at most max_items are written),
+ * or -1 on bad arguments.  Host-only. */
+SCD_API int scd_name_topk_plan_pair(int64_t N, int64_t V, int k, int pair, int32_t* out_items_x4 /* host */, int max_items);
 SCD_API int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, int64_t V, float scale, int k,
                   int want_softmax, int64_t idx_offset, float* vals, int64_t* idx,
                   float* row_max, float* row_sumexp, void* ws, size_t ws_bytes, scd_stream_t stream);
@@ -193,6 +197,32 @@ SCD_API int scd_label_histogram(const int64_t* labels, int64_t N, int K, int32_t
  * input.', :349-350).  Host-only: no stream, no device memory. */
 SCD_API int scd_constrained_assign(const int32_t* cost, int64_t N, int K, int64_t size_min, int64_t size_max,
                            int32_t* labels, int64_t* total_cost /* nullable */, int64_t* n_augment /* nullable */);
+
+/* ---------------------------------------------------------------- multi-GPU exchange over NVLink peer memory */
+
+/* The reference is single-GPU (no distributed call site); these entry points exist because north_star shards
+ * the path.  One process per GPU; every rank allocates an exchange buffer and a flag pad in peer-mappable memory and
+ * passes HOST tables of the G mapped device pointers (index = rank; scd_b200/peer.py builds them with torch symmetric
+ * memory).  `channel` (0..7) selects one of the pad's independent barrier counters; all ranks must issue the same
+ * sequence of calls per channel.  Waits are bounded (4 s) and trap with a message instead of hanging. */
+SCD_API size_t scd_peer_flag_bytes(void);                 /* bytes of a flag pad; the caller zeroes it once, before first use */
+SCD_API size_t scd_peer_mstep_bytes(int K, int D);        /* bytes of one M-step exchange block: [K*D sums f32 | K counts i32 | pad | inertia f64] */
+SCD_API int scd_peer_barrier(void* const* peer_flags, int world, int rank, int channel, scd_stream_t stream);
+/* local_utils/faster_mix_k_means_pytorch.py:61-64 + :71 over row shards: the all-reduce of the per-rank
+ * [sums | counts | inertia] blocks (at byte offset buf_byte_offset of every rank's exchange buffer, filled by
+ * scd_mstep_sums / scd_estep writing straight into it) fused with scd_finalize_centers: flag barrier, peer loads added in
+ * rank order (bitwise identical centres on every rank), divide, move norms, next E-step operands.  counts_out (nullable,
+ * [K] fp32) / inertia_out (nullable, fp64 scalar): the reduced counts and inertia. */
+SCD_API int scd_finalize_centers_peer(void* const* peer_bufs, void* const* peer_flags, int world, int rank, int channel,
+                              size_t buf_byte_offset, const float* C_old /* nullable */, float* C_new,
+                              float* move_norms /* nullable, [K] */, float* counts_out, double* inertia_out, int K, int D,
+                              void* estep_ws /* nullable */, size_t estep_ws_bytes, scd_stream_t stream);
+/* main_unsup.py:575-577 over row shards: scd_pack_vote_records whose stores ARE the all-gather - record i of this rank goes
+ * to row (row_offset + i) of the [N_total, 1 + k_used] int32 array at buf_byte_offset of EVERY rank's exchange buffer.
+ * Follow with scd_peer_barrier before scd_vote_records reads the local copy. */
+SCD_API int scd_pack_vote_records_peer(void* const* peer_bufs, int world, int rank, size_t buf_byte_offset, const int64_t* labels,
+                               const int64_t* topk_idx, int k_total, int k_used, int64_t n, int64_t row_offset,
+                               scd_stream_t stream);
 
 /* ---------------------------------------------------------------- evaluation either side of the path */
 

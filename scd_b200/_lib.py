@@ -35,6 +35,7 @@ SIGNATURES = {
     'scd_gather_rows_bf16': (_int, [_vp, _vp, _int, _int, _i64, _vp, _vp]),
     'scd_name_topk_workspace_bytes': (_sz, [_i64, _i64, _int]),
     'scd_name_topk_plan': (_int, [_i64, _i64, _int, _vp]),
+    'scd_name_topk_plan_pair': (_int, [_i64, _i64, _int, _int, _vp, _int]),
     'scd_name_topk': (_int, [_vp, _i64, _int, _vp, _i64, _f32, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'scd_topk_merge': (_int, [_vp, _vp, _vp, _vp, _int, _i64, _int, _f32, _int, _vp, _vp, _vp]),
     'scd_vote_workspace_bytes': (_sz, [_i64, _int]),
@@ -43,6 +44,11 @@ SIGNATURES = {
     'scd_vote_presorted': (_int, [_vp, _int, _int, _vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'scd_pack_vote_records': (_int, [_vp, _vp, _int, _int, _i64, _vp, _vp]),
     'scd_vote_records': (_int, [_vp, _int, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+    'scd_peer_flag_bytes': (_sz, []),
+    'scd_peer_mstep_bytes': (_sz, [_int, _int]),
+    'scd_peer_barrier': (_int, [_vp, _int, _int, _int, _vp]),
+    'scd_finalize_centers_peer': (_int, [_vp, _vp, _int, _int, _int, _sz, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _vp]),
+    'scd_pack_vote_records_peer': (_int, [_vp, _int, _int, _sz, _vp, _vp, _int, _int, _i64, _i64, _vp]),
     'scd_label_histogram': (_int, [_vp, _i64, _int, _vp, _vp]),
     'scd_constrained_assign': (_int, [_vp, _i64, _int, _i64, _i64, _vp, C.POINTER(_i64), C.POINTER(_i64)]),
     'scd_contingency': (_int, [_vp, _int, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp]),

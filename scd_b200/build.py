@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB = os.path.join(PKG, 'libscd_b200.so')
 SOURCES = [os.path.join(CSRC, 'scd_api.cu'), os.path.join(CSRC, 'hungarian.cpp'), os.path.join(CSRC, 'constrained.cpp')]
-HEADERS = [os.path.join(CSRC, f) for f in ('ptx.cuh', 'naming_kernel.cuh', 'kmeans_kernel.cuh', 'estep_tc_kernel.cuh', 'vote_kernel.cuh', 'eval_kernel.cuh')] + \
+HEADERS = [os.path.join(CSRC, f) for f in ('ptx.cuh', 'peer_kernel.cuh', 'naming_kernel.cuh', 'kmeans_kernel.cuh', 'estep_tc_kernel.cuh', 'vote_kernel.cuh', 'eval_kernel.cuh')] + \
           [os.path.join(os.path.dirname(PKG), 'include', 'scd_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']

@@ -84,26 +84,57 @@ static_assert(NameSmem::total + 1024 <= 232448, "exceeds 227 KB of shared memory
 struct NameParams {
   long long n_rows;        // N
   long long v_total;       // V (this rank's vocabulary slice length)
-  // work items: row blocks [0, n_full_rb) sweep the whole vocabulary in one item each; the remaining
-  // (tail-wave) row blocks are split into n_vsplit vocabulary chunks so the last wave fills the GPU
-  int n_full_rb;
-  int n_vsplit;            // vocabulary chunks per tail row block (also the number of partial-result slots)
-  int tiles_per_chunk;     // 256-wide tiles per chunk
+  // work partition: the (row block, vocabulary tile) space, row-block major, is cut into one contiguous range of
+  // tiles per CTA pair (NameWork); a range covers the end of one row block, whole row blocks, and the start of another.
+  // Each piece of a row block is a work item; its result goes to partial-list slot `piece ordinal within the row block`.
+  long long work_total;    // n_row_blocks * tiles_total
+  int tiles_total;         // ceil(V / kTileN)
   int n_row_blocks;        // ceil(N / 256)
   int num_kb;              // ceil(D / 64) live A k-blocks (TMA zero-fills the ragged end of D)
   int want_softmax;
   float scale_log2e;       // scale * log2(e) for the running sum-exp
-  // partial results, one slot per (vocabulary chunk, column half): [n_vsplit * 2][N][KT] / [n_vsplit * 2][N]
-  // (part_idx is pre-set to -1: slots a row never writes are skipped by the merge)
+  // partial results, one slot per (piece of the row block, column half): [n_slots * 2][N][KT] / [n_slots * 2][N]
+  // (the merge derives the number of pieces of a row block from the same NameWork arithmetic)
   float* part_val;
   int* part_idx;
   float* part_max;
   float* part_sum;
-  float* scratch;          // [gridDim.x][2 halves][128 rows][KT slots][32] parked chunks
+  float* scratch;          // [gridDim.x][2 halves][4 warps][KT slots][8][32 lanes] float4: parked chunks, lane-interleaved
   long long* prof;         // nullable: [pairs][16] cycle counters (scd_debug_set_name_profile), debugging aid
   const __nv_bfloat16* x;  // [N, d] row-major: the loader warps read the TMEM-resident k-blocks straight from global memory
   int d;
 };
+
+// Linear partition of the work: tile index l = row_block * T + tile; pair q of P owns [bound(q), bound(q + 1)).
+// Loads differ by at most one tile between pairs, and a pair starts at most (range / T + 2) work items - at N = 8 ranks
+// (63 row blocks on 74 pairs) that is two items of ~40 tiles instead of six of 14, each of which paid the item
+// start-up and the final exact scan.
+struct NameWork {
+  long long W;   // work_total
+  int T;         // tiles per row block
+  int P;         // pairs
+  __host__ __device__ long long bound(int q) const { return (W * q) / P; }
+  __host__ __device__ int owner(long long l) const {       // the pair whose range holds tile l (0 <= l < W)
+    int q = (int)(((l + 1) * P + W - 1) / W) - 1;          // largest q with bound(q) <= l
+    while (q + 1 < P && bound(q + 1) <= l) ++q;
+    while (q > 0 && bound(q) > l) --q;
+    return q;
+  }
+  // pieces a row block is cut into (1 when one pair sweeps it whole)
+  __host__ __device__ int pieces(int rb) const { return owner((long long)(rb + 1) * T - 1) - owner((long long)rb * T) + 1; }
+};
+
+struct NameItem { int rb, t0, nt, part; };
+
+// the work item of pair q that starts at tile l of its range [.., hi)   (work_total < 2^31, checked by the host)
+__host__ __device__ inline NameItem name_item_at(const NameWork& w, int q, int l, int hi) {
+  NameItem it;
+  it.rb = l / w.T;
+  it.t0 = l - it.rb * w.T;
+  it.nt = hi - l < w.T - it.t0 ? hi - l : w.T - it.t0;
+  it.part = it.t0 == 0 ? 0 : q - w.owner((long long)it.rb * w.T);
+  return it;
+}
 
 // One sorted top-KT list in registers, ordered by (value descending, column ascending) - the order
 // torch.topk(..., largest=True, sorted=True) yields when ties resolve to the lower index.  Columns may
@@ -178,8 +209,8 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const bool leader = cta_rank == 0;
   const int pair = blockIdx.x >> 1;
   const int n_pairs = gridDim.x >> 1;
-  const int n_items = p.n_full_rb + (p.n_row_blocks - p.n_full_rb) * p.n_vsplit;
-  const int tiles_total = (int)((p.v_total + kTileN - 1) / kTileN);
+  const NameWork work{p.work_total, p.tiles_total, n_pairs};
+  const int l_lo = (int)work.bound(pair), l_hi = (int)work.bound(pair + 1);      // this pair's range of tiles
 
   const int nkb = p.num_kb;
   const int nkb_tmem = min(nkb, kTmemAKBlocks);
@@ -217,25 +248,14 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + NameSmem::tmem_ptr);
 
-  // work item -> (row block, first tile, tile count)
-  auto item_rb = [&](int it) { return it < p.n_full_rb ? it : p.n_full_rb + (it - p.n_full_rb) / p.n_vsplit; };
-  auto item_chunk = [&](int it) { return it < p.n_full_rb ? 0 : (it - p.n_full_rb) % p.n_vsplit; };
-  auto item_tile0 = [&](int it) { return item_chunk(it) * p.tiles_per_chunk; };
-  auto item_ntiles = [&](int it) {
-    if (it < p.n_full_rb) return tiles_total;
-    int t0 = item_tile0(it);
-    int t1 = min(t0 + p.tiles_per_chunk, tiles_total);
-    return max(t1 - t0, 0);
-  };
   // Staggered sweep: pair q starts its walk over an item's tiles at a different offset and wraps around, so
   // at any moment the 74 pairs read 74 different vocabulary tiles (spread over all L2 slices) instead of
   // all hammering the same lines.  The result does not depend on the visiting order (explicit tie rules).
-  auto item_tile = [&](int it, int t) {
-    const int nt = item_ntiles(it);
-    const int start = (int)(((long long)pair * nt) / n_pairs);
+  auto item_tile = [&](const NameItem& it, int t) {
+    const int start = (int)(((long long)pair * it.nt) / n_pairs);
     int tt = t + start;
-    if (tt >= nt) tt -= nt;
-    return item_tile0(it) + tt;
+    if (tt >= it.nt) tt -= it.nt;
+    return it.t0 + tt;
   };
 
   if (warp == 0 || warp == 2) {
@@ -246,8 +266,10 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     uint32_t g = 0;
     const bool prof = p.prof != nullptr;
     long long pf_t0 = prof ? clock64() : 0, pf_e = 0;
-    for (int it = pair; it < n_items; it += n_pairs) {
-      const int nt = item_ntiles(it);
+    for (int l = l_lo; l < l_hi;) {
+      const NameItem it = name_item_at(work, pair, l, l_hi);
+      l += it.nt;
+      const int nt = it.nt;
       for (int t = 0; t < nt; ++t) {
         const int v0 = item_tile(it, t) * kTileN + (int)cta_rank * (kTileN / 2);
         for (int kb = 0; kb < nkb; ++kb, ++g) {
@@ -278,8 +300,10 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const uint32_t quad = warp & 3u;
     const uint32_t lane_addr = (quad * 32u) << 16;
     int my_item_no = 0;
-    for (int it = pair; it < n_items; it += n_pairs, ++my_item_no) {
-      const long long row = (long long)item_rb(it) * 2 * kBlockM + cta_rank * kBlockM + quad * 32 + lane;
+    for (int l = l_lo; l < l_hi; ++my_item_no) {
+      const NameItem it = name_item_at(work, pair, l, l_hi);
+      l += it.nt;
+      const long long row = (long long)it.rb * 2 * kBlockM + cta_rank * kBlockM + quad * 32 + lane;
       const uint4* src = reinterpret_cast<const uint4*>(p.x + (size_t)(row < p.n_rows ? row : 0) * p.d);
       for (int kb = 0; kb < nkb_tmem; ++kb) {
         uint32_t r[32];
@@ -300,7 +324,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       // warp 12 is also the TMA producer of the shared-memory A k-blocks: k-block kb >= kTmemAKBlocks of the NEXT item
       // is loaded as soon as the last tile of the current item has consumed it (a_empty, committed by the MMA issuer)
       if (warp == 12) {
-        const int row0 = item_rb(it) * 2 * kBlockM + (int)cta_rank * kBlockM;
+        const int row0 = it.rb * 2 * kBlockM + (int)cta_rank * kBlockM;
         for (int kb = kTmemAKBlocks; kb < nkb; ++kb) {
           ptx::mbar_wait(a_empty_bar(kb), (my_item_no & 1) ^ 1, 100 + kb);
           if (ptx::elect_one()) {
@@ -329,14 +353,15 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const uint32_t idesc = ptx::make_idesc_bf16_f32(2 * kBlockM, kTileN);
       uint32_t g = 0, tile_no = 0;
       int my_item_no = 0;
-      long long g_total = 0;
-      for (int it = pair; it < n_items; it += n_pairs) g_total += (long long)item_ntiles(it) * nkb;
+      const long long g_total = (long long)(l_hi - l_lo) * nkb;
       const bool prof = p.prof != nullptr && me == 0;
       long long pf_t0 = prof ? clock64() : 0, pf_te = 0, pf_a = 0, pf_b = 0, pf_tok = 0;
       long long* const trace = (p.prof != nullptr && pair == 0 && me < 2) ? p.prof + (size_t)n_pairs * 32 + me * 384 : nullptr;
       int n_ev = 0;
-      for (int it = pair; it < n_items; it += n_pairs, ++my_item_no) {
-        const int nt = item_ntiles(it);
+      for (int l = l_lo; l < l_hi; ++my_item_no) {
+        const NameItem it = name_item_at(work, pair, l, l_hi);
+        l += it.nt;
+        const int nt = it.nt;
         for (int t = 0; t < nt; ++t, ++tile_no) {
           const uint32_t buf = tile_no & 1u;
           const uint32_t d_tmem = tmem_base + buf * kAccStride;
@@ -407,13 +432,6 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             if (trace && lane == 0 && n_ev < 128) { trace[3 * n_ev] = tr0; trace[3 * n_ev + 1] = tr1; trace[3 * n_ev + 2] = clock64(); ++n_ev; }
           }
         }
-        if (nt == 0 && me == 0) {       // an item without tiles still has to hand its A buffers back
-          for (int kb = 0; kb < nkb; ++kb) {
-            ptx::mbar_wait(a_full_bar(kb), my_item_no & 1, 450 + kb);
-            if (ptx::elect_one()) ptx::umma_commit<2>(a_empty_bar(kb), 0b11);
-            __syncwarp();
-          }
-        }
       }
       if (prof && lane == 0) {
         long long* o = p.prof + (size_t)pair * 32;
@@ -427,16 +445,21 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const uint32_t lane_addr = (quad * 32u) << 16;
     uint32_t tile_no = 0;
     ChunkTop<KT> ctop;
+    // parked chunks of this warp's 32 rows: [KT slots][8 float4][32 lanes] - lane-interleaved, so a warp reading one
+    // slot of all its rows touches 4 lines per instruction (the per-thread layout of round 1 touched 32: the exact scan
+    // was bound by the load/store unit, ~20 k cycles per work item)
     float4* const my_scratch = reinterpret_cast<float4*>(p.scratch) +
-                               (((size_t)blockIdx.x * kEpiHalves + half) * kBlockM + quad * 32 + lane) * KT * 8;   // KT slots x 8 float4
+                               ((((size_t)blockIdx.x * kEpiHalves + half) * 4 + quad) * KT * 8) * 32 + lane;
     const bool prof = p.prof != nullptr && warp == 4 && leader;
     long long pf_t0 = prof ? clock64() : 0, pf_w = 0, pf_fin = 0;
     long long* const trace = (prof && pair == 0) ? p.prof + (size_t)n_pairs * 32 + 2 * 384 : nullptr;
     int n_ev = 0;
     int epi_item_no = 0;
-    for (int it = pair; it < n_items; it += n_pairs, ++epi_item_no) {
-      const int nt = item_ntiles(it);
-      const long long row = (long long)item_rb(it) * 2 * kBlockM + cta_rank * kBlockM + quad * 32 + lane;
+    for (int l = l_lo; l < l_hi; ++epi_item_no) {
+      const NameItem it = name_item_at(work, pair, l, l_hi);
+      l += it.nt;
+      const int nt = it.nt;
+      const long long row = (long long)it.rb * 2 * kBlockM + cta_rank * kBlockM + quad * 32 + lane;
       long long* const itrace = (prof && pair == 0 && lane == 0 && epi_item_no < 64) ? p.prof + (size_t)n_pairs * 32 + 4 * 384 + epi_item_no * 6 : nullptr;
       ctop.reset();
       float run_max = -INFINITY, run_sum = 0.f;
@@ -462,10 +485,10 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           run_sum += acc;
         }
         if (ctop.admits(cmax, colbase)) {
-          float4* dst = my_scratch + ctop.slot[KT - 1] * 8;
+          float4* dst = my_scratch + ctop.slot[KT - 1] * (8 * 32);
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+            dst[q * 32] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
                                  __uint_as_float(r[4 * q + 3]));
           ctop.insert_last(cmax, colbase);
         }
@@ -512,9 +535,10 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       // and on real score distributions there are k .. k + 3 of them among the KT * 32 parked values.
       //  1. one pass over the parked chunks (next chunk's loads in flight behind the current one's compares) builds a
       //     32-bit survivor mask per chunk - no value is kept, no local memory is touched;
-      //  2. the first survivor of every chunk is re-read from the scratch slot (KT independent loads in flight) and
-      //     pushed, then a short lock-step loop drains the few remaining bits.
-      // ~1 k warp-instructions and ~2-3 k cycles per work item, which hides behind the two tiles the issuers can run
+      //  2. the first KT + 4 survivors (normally all of them) are re-read from the scratch slots with independent loads -
+      //     one L2 round trip - and pushed; a lock-step loop drains what is left (flat score distributions only).
+      // Round 2 start: the drain loop did one DEPENDENT L2 load per extra survivor of the warp's worst lane, ~22 k cycles
+      // per item (profiles/r2b_name_item_timeline.txt) of which ~11 k hide behind the two tiles the issuers can run
       // ahead into the double-buffered accumulators.  (Round 1 appended survivors to per-thread candidate lists in
       // local memory: divergent st.local, ~28 k cycles per item with the tensor pipe idle for ~18 k of them - 4 % of a
       // whole-vocabulary sweep but 20-37 % of the short items a small row shard is cut into)
@@ -524,14 +548,23 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       top.reset();
       {
         const float keep_from = ctop.m[KT - 1];
+        // first column of the chunk parked in PHYSICAL slot e (-1: empty); the scan walks the slots in physical order -
+        // every lane reads the same slot, and the order of the pushes does not matter (explicit tie rules)
+        int scol[KT];
+#pragma unroll
+        for (int e = 0; e < KT; ++e) {
+          scol[e] = -1;
+#pragma unroll
+          for (int f = 0; f < KT; ++f) if (ctop.slot[f] == e) scol[e] = ctop.col[f];
+        }
         uint32_t mask[KT];
         float4 xa[8], xb[8];
         auto load_chunk = [&](int e, float4 (&x)[8]) {
-          const float4* src = my_scratch + ctop.slot[e] * 8;
+          const float4* src = my_scratch + e * (8 * 32);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) x[q] = ctop.col[e] >= 0 ? src[q] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          for (int q = 0; q < 8; ++q) x[q] = src[q * 32];
         };
-        auto survivors = [&](const float4 (&x)[8]) {
+        auto survivors = [&](const float4 (&x)[8], int col) {
           uint32_t m = 0u;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -540,29 +573,40 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             for (int w = 0; w < 4; ++w)
               if (xv[w] >= keep_from && xv[w] > -INFINITY) m |= 1u << (4 * q + w);
           }
-          return m;
+          return col >= 0 ? m : 0u;              // an empty slot holds stale values
         };
         load_chunk(0, xa);
 #pragma unroll
         for (int e = 0; e < KT; ++e) {
           if (e + 1 < KT) { if (e & 1) load_chunk(e + 1, xa); else load_chunk(e + 1, xb); }
-          mask[e] = (e & 1) ? survivors(xb) : survivors(xa);
+          mask[e] = (e & 1) ? survivors(xb, scol[e]) : survivors(xa, scol[e]);
         }
-        // first survivor of every chunk: KT independent scalar re-reads in flight, then KT pushes
-        float v0[KT];
-        int c0[KT];
+        // every survivor of the row in ONE round trip: kGather independent scalar re-reads (lowest slot, lowest
+        // column first), then the pushes.  kGather = KT + 4 covers what real score distributions leave (k .. k + 3).
+        const float* const my_scalars = reinterpret_cast<const float*>(my_scratch);
+        auto parked = [&](int slot, int j) { return my_scalars[((slot * 8 + (j >> 2)) * 32) * 4 + (j & 3)]; };
+        constexpr int kGather = KT + 4;
+        float gv[kGather];
+        int gc[kGather];
 #pragma unroll
-        for (int e = 0; e < KT; ++e) {
-          const bool live = mask[e] != 0u;
-          const int j = live ? __ffs((int)mask[e]) - 1 : 0;
-          const float* src = reinterpret_cast<const float*>(my_scratch + ctop.slot[e] * 8);
-          v0[e] = live ? src[j] : -INFINITY;
-          c0[e] = live ? ctop.col[e] + j : -1;
-          mask[e] &= mask[e] - 1u;                    // 0 stays 0
+        for (int s2 = 0; s2 < kGather; ++s2) {
+          uint32_t m = 0u;
+          int slot_sel = 0, col_sel = 0;
+#pragma unroll
+          for (int e = KT - 1; e >= 0; --e)
+            if (mask[e] != 0u) { m = mask[e]; slot_sel = e; col_sel = scol[e]; }
+          const bool live = m != 0u;
+          const int j = live ? __ffs((int)m) - 1 : 0;
+          gv[s2] = live ? parked(slot_sel, j) : -INFINITY;
+          gc[s2] = live ? col_sel + j : -1;
+          bool cleared = false;
+#pragma unroll
+          for (int e = 0; e < KT; ++e)
+            if (!cleared && mask[e] != 0u) { mask[e] &= mask[e] - 1u; cleared = true; }
         }
 #pragma unroll
-        for (int e = 0; e < KT; ++e) top.push(v0[e], c0[e]);
-        // the rest (usually nothing, or one or two bits in a warp): lock-step, lowest chunk first
+        for (int s2 = 0; s2 < kGather; ++s2) top.push(gv[s2], gc[s2]);
+        // the rest (ties at the threshold / flat score distributions; normally nothing): lock-step, lowest slot first
         uint32_t left = 0u;
 #pragma unroll
         for (int e = 0; e < KT; ++e) left |= mask[e];
@@ -572,10 +616,10 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           int slot_sel = 0, col_sel = 0;
 #pragma unroll
           for (int e = KT - 1; e >= 0; --e)
-            if (mask[e] != 0u) { m = mask[e]; slot_sel = ctop.slot[e]; col_sel = ctop.col[e]; }
+            if (mask[e] != 0u) { m = mask[e]; slot_sel = e; col_sel = scol[e]; }
           const bool live = m != 0u;
           const int j = live ? __ffs((int)m) - 1 : 0;
-          const float v = live ? reinterpret_cast<const float*>(my_scratch + slot_sel * 8)[j] : -INFINITY;
+          const float v = live ? parked(slot_sel, j) : -INFINITY;
           top.push(v, live ? col_sel + j : -1);
           bool cleared = false;
           left = 0u;
@@ -588,7 +632,7 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
       if (itrace) itrace[3] = clock64();                                                        // exact scan done
       if (row < p.n_rows) {
-        const long long slot = (long long)(item_chunk(it) * kEpiHalves + (int)half) * p.n_rows + row;
+        const long long slot = (long long)(it.part * kEpiHalves + (int)half) * p.n_rows + row;
 #pragma unroll
         for (int j = 0; j < KT; ++j) { p.part_val[slot * KT + j] = top.v[j]; p.part_idx[slot * KT + j] = top.i[j]; }
         p.part_max[slot] = run_max;
@@ -618,9 +662,12 @@ __global__ void topk_merge_kernel(const float* __restrict__ part_val, const IdxT
                                   const float* __restrict__ part_max, const float* __restrict__ part_sum,
                                   int parts, long long n_rows, int kt_in, int k_out, float scale, int want_softmax,
                                   long long idx_offset, float* __restrict__ out_val, long long* __restrict__ out_idx,
-                                  float* __restrict__ out_max, float* __restrict__ out_sum) {
+                                  float* __restrict__ out_max, float* __restrict__ out_sum, const NameWork work) {
   const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n_rows) return;
+  // lists of one launch of name_topk_kernel: a row block has pieces(rb) pieces x 2 column halves (work.P > 0);
+  // all-gathered vocabulary shards: `parts` lists for every row
+  if (work.P > 0) parts = work.pieces((int)(row / (2 * kBlockM))) * kEpiHalves;
   float bv[8]; long long bi[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { bv[j] = -INFINITY; bi[j] = -1; }

@@ -1,0 +1,214 @@
+// Exchange steps of the sharded path over NVLink peer memory, fused with the kernels that follow them.
+//
+// One process per GPU; every rank maps the others' exchange buffers into its own address space (torch symmetric
+// memory: cuMem allocations exported / imported once per fit, scd_b200/peer.py).  Two exchanges exist on the path:
+//
+//   * k-means M-step (faster_mix_k_means_pytorch.py:61-64 over sharded rows): every rank's segment sum leaves
+//     [K*D sums | K counts | inertia] in ITS buffer; finalize_centers_peer_kernel is the all-reduce AND the divide: after
+//     a flag barrier it reads the G buffers with peer loads, adds them in rank order (bitwise the same centres on every
+//     rank) and writes centres, move norms and the next E-step's operands.  No pack kernel, no NCCL launch, no second
+//     pass over the reduced buffer.
+//   * vote (main_unsup.py:575-577 over sharded rows): pack_vote_records_peer_kernel stores the rank's
+//     [label, name_0 .. name_(k-1)] int32 records straight into every rank's gathered array (the all-gather is the
+//     store); peer_barrier_kernel orders it against the vote.
+//
+// Flags: each rank owns a pad of 32-bit words, written remotely by its peers.  Channel c:
+//     arrive[c][r]  (r = 0 .. G-1)   epoch rank r has reached on channel c   (written by rank r, read locally)
+//     epoch[c], ticket[c]            local bookkeeping (only this rank touches them)
+// A barrier = store (my epoch + 1) into arrive[c][me] of every peer, then wait until all G local arrive words have
+// reached it.  Epochs live on the device, so a captured CUDA graph replays correctly.  Every wait is bounded by wall
+// clock and traps with a message instead of hanging the GPU (a rank that died, or ranks launching different sequences).
+#pragma once
+#include "ptx.cuh"
+#include <cuda_bf16.h>
+
+namespace scd {
+
+constexpr int kPeerMaxWorld = 16;
+constexpr int kPeerChannels = 8;
+constexpr int kPeerChannelWords = 32;            // arrive[16] | epoch | ticket | pad
+constexpr int kPeerFlagWords = kPeerChannels * kPeerChannelWords;
+
+struct PeerPtrs {                                 // by value in the kernel parameters
+  void* buf[kPeerMaxWorld];                       // rank r's exchange buffer, mapped here
+  unsigned* flags[kPeerMaxWorld];                 // rank r's flag pad, mapped here
+  int world, rank;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {       // never served from a stale L1 line
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_peer_f1(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_peer_i1(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_peer_d1(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __noinline__ void peer_timeout_trap(int channel, int from_rank, unsigned have, unsigned want) {
+  printf("[scd_b200] peer barrier timed out: block %d channel %d waiting for rank %d (flag %u, want %u)\n", (int)blockIdx.x,
+         channel, from_rank, have, want);
+  __trap();
+}
+
+// the epoch this launch has to reach on `channel` (every block of the launch reads the same value: it only moves when the
+// launch's last block calls peer_finish)
+__device__ __forceinline__ unsigned peer_target(const PeerPtrs& pp, int channel) {
+  return *reinterpret_cast<volatile unsigned*>(pp.flags[pp.rank] + channel * kPeerChannelWords + kPeerMaxWorld) + 1u;
+}
+// threads [0, world) of ONE block of the launch: everything this rank wrote before (earlier kernels of the stream, or this
+// block after a __syncthreads) becomes visible to a peer that sees the flag
+__device__ __forceinline__ void peer_signal(const PeerPtrs& pp, int channel, unsigned target) {
+  if ((int)threadIdx.x < pp.world) {
+    __threadfence_system();
+    st_release_sys(pp.flags[threadIdx.x] + channel * kPeerChannelWords + pp.rank, target);
+  }
+}
+// threads [0, world) of every block that is going to read peer data; ends with a block barrier
+__device__ __forceinline__ void peer_wait(const PeerPtrs& pp, int channel, unsigned target) {
+  if ((int)threadIdx.x < pp.world) {
+    const unsigned* f = pp.flags[pp.rank] + channel * kPeerChannelWords + threadIdx.x;
+    unsigned v = ld_acquire_sys(f);
+    if ((int)(v - target) < 0) {
+      ptx::WaitClock clk;
+      while ((int)((v = ld_acquire_sys(f)) - target) < 0) {
+        if (clk.expired()) peer_timeout_trap(channel, (int)threadIdx.x, v, target);
+        __nanosleep(20);
+      }
+    }
+  }
+  __syncthreads();
+}
+// last block of the launch publishes the new epoch (ticket counts the blocks that are done with the channel)
+__device__ __forceinline__ void peer_finish(const PeerPtrs& pp, int channel, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* base = pp.flags[pp.rank] + channel * kPeerChannelWords + kPeerMaxWorld;
+    __threadfence();
+    if (atomicAdd(base + 1, 1u) == gridDim.x * gridDim.y - 1u) {
+      base[1] = 0u;
+      *reinterpret_cast<volatile unsigned*>(base) = target;
+      __threadfence();
+    }
+  }
+}
+
+// plain barrier between two kernels of the stream (one block)
+__global__ void peer_barrier_kernel(const PeerPtrs pp, int channel) {
+  const unsigned target = peer_target(pp, channel);
+  peer_signal(pp, channel, target);
+  peer_wait(pp, channel, target);
+  peer_finish(pp, channel, target);
+}
+
+// ---------------------------------------------------------------------------------------------
+// All-reduce + divide of the row-sharded M-step.  Exchange buffer of a rank (fp32 words unless noted):
+//     [K*D sums | K counts (int32) | pad to 8 B | inertia (fp64)]          (peer_mstep_words)
+// One block per cluster, as finalize_centers_kernel; block 0 also leaves the summed inertia in *inertia_out.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t peer_mstep_inertia_word(int K, int D) { return (((size_t)K * D + K + 1) / 2) * 2; }
+__host__ __device__ inline size_t peer_mstep_words(int K, int D) { return peer_mstep_inertia_word(K, D) + 2; }
+
+__global__ void __launch_bounds__(256)
+finalize_centers_peer_kernel(const PeerPtrs pp, int channel, size_t buf_word_offset, const float* __restrict__ c_old,
+                             float* __restrict__ c_new, float* __restrict__ move_norm, float* __restrict__ counts_out,
+                             double* __restrict__ inertia_out, int K, int D, __nv_bfloat16* __restrict__ plane_hi,
+                             __nv_bfloat16* __restrict__ plane_lo, float* __restrict__ cnorm) {
+  const unsigned target = peer_target(pp, channel);
+  if (blockIdx.x == 0) peer_signal(pp, channel, target);
+  peer_wait(pp, channel, target);
+
+  const int k = blockIdx.x;
+  const int G = pp.world;
+  int cnt_i = 0;
+  for (int r = 0; r < G; ++r)
+    cnt_i += ld_peer_i1(reinterpret_cast<const int*>(reinterpret_cast<const float*>(pp.buf[r]) + buf_word_offset + (size_t)K * D) + k);
+  const float cnt = (float)cnt_i;
+  if (threadIdx.x == 0 && counts_out) counts_out[k] = cnt;
+  if (k == 0 && threadIdx.x == 0 && inertia_out) {
+    double t = 0.0;
+    for (int r = 0; r < G; ++r)
+      t += ld_peer_d1(reinterpret_cast<const double*>(reinterpret_cast<const float*>(pp.buf[r]) + buf_word_offset + peer_mstep_inertia_word(K, D)));
+    *inertia_out = t;
+  }
+  float part = 0.f, npart = 0.f;
+  const bool vec = (D & 3) == 0;
+  for (int d4 = threadIdx.x * 4; d4 < D; d4 += blockDim.x * 4) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    const int nd = min(4, D - d4);
+    for (int r = 0; r < G; ++r) {                      // fixed rank order: identical bits on every rank
+      const float* src = reinterpret_cast<const float*>(pp.buf[r]) + buf_word_offset + (size_t)k * D + d4;
+      if (vec) { const float4 v = ld_peer_f4(src); s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w; }
+      else for (int q = 0; q < nd; ++q) s[q] += ld_peer_f1(src + q);
+    }
+    for (int q = 0; q < nd; ++q) {
+      const int d = d4 + q;
+      const float c = s[q] / cnt;                      // 0 / 0 -> NaN row, as torch's mean over zero rows
+      c_new[(size_t)k * D + d] = c;
+      if (c_old) { const float df = c - c_old[(size_t)k * D + d]; part += df * df; }
+      if (plane_hi) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(c);
+        plane_hi[(size_t)k * D + d] = h;
+        plane_lo[(size_t)k * D + d] = __float2bfloat16_rn(c - __bfloat162float(h));
+      }
+    }
+  }
+  // ||c||^2 of the next E-step must have centroid_split_kernel's summation order (thread t owns d = t, t + 256, ..): a
+  // second, cheap pass over the row this block has just written
+  __syncthreads();
+  if (plane_hi)
+    for (int d = threadIdx.x; d < D; d += blockDim.x) { const float c = c_new[(size_t)k * D + d]; npart = fmaf(c, c, npart); }
+  __shared__ float sh[32], shn[32];
+  for (int off = 16; off > 0; off >>= 1) {
+    part += __shfl_down_sync(0xffffffffu, part, off);
+    npart += __shfl_down_sync(0xffffffffu, npart, off);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = part; shn[threadIdx.x >> 5] = npart; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f, tn = 0.f;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) { t += sh[w]; tn += shn[w]; }
+    if (move_norm) move_norm[k] = sqrtf(t);
+    if (cnorm) cnorm[k] = tn;
+  }
+  peer_finish(pp, channel, target);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The all-gather of the vote records IS the store: rec[g] = [label, name_0 .. name_(k-1)] (int32) of global row
+// g = row_offset + i goes to every rank's gathered array.
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_vote_records_peer_kernel(const PeerPtrs pp, size_t buf_byte_offset, const long long* __restrict__ labels,
+                                              const long long* __restrict__ idx, int k_total, int k_used, long long n,
+                                              long long row_offset) {
+  const int w = 1 + k_used;
+  const long long total = n * w;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / w;
+    const int j = (int)(t - i * w);
+    const int v = j == 0 ? (int)labels[i] : (int)idx[i * k_total + (j - 1)];
+    for (int r = 0; r < pp.world; ++r)
+      reinterpret_cast<int*>(reinterpret_cast<char*>(pp.buf[r]) + buf_byte_offset)[row_offset * w + t] = v;
+  }
+}
+
+}  // namespace scd

@@ -20,6 +20,7 @@
 #include "naming_kernel.cuh"
 #include "vote_kernel.cuh"
 #include "eval_kernel.cuh"
+#include "peer_kernel.cuh"
 
 namespace {
 
@@ -129,11 +130,10 @@ struct NamePlan {
   int kt;                 // compiled list length (1, 5 or 8)
   int n_row_blocks;
   int tiles_total;
-  int n_full_rb;          // row blocks that sweep the whole vocabulary as one work item
-  int n_vsplit;           // vocabulary chunks of the remaining (tail-wave) row blocks
-  int tiles_per_chunk;
   int n_pairs;
-  size_t off_val, off_idx, off_max, off_sum, off_scratch, idx_bytes, bytes;
+  int n_slots;            // most pieces any row block is cut into (partial-list slots per row and column half)
+  long long work_total;   // n_row_blocks * tiles_total
+  size_t off_val, off_idx, off_max, off_sum, off_scratch, bytes;
 };
 
 bool plan_naming(int64_t N, int64_t V, int k, NamePlan* pl) {
@@ -141,33 +141,38 @@ bool plan_naming(int64_t N, int64_t V, int k, NamePlan* pl) {
   pl->kt = k == 1 ? 1 : (k <= 5 ? 5 : 8);
   pl->n_row_blocks = (int)((N + 2 * scd::kBlockM - 1) / (2 * scd::kBlockM));
   pl->tiles_total = (int)((V + scd::kTileN - 1) / scd::kTileN);
+  pl->work_total = (long long)pl->n_row_blocks * pl->tiles_total;
+  if (pl->work_total >= (1ll << 31)) return false;
   const int pairs_hw = std::max(1, device_sm_count() / 2);
-  // Whole waves of row blocks keep the vocabulary sweep in one piece (the running top-k threshold stays
-  // warm, which is what makes the epilogue cheap); only the last, partial wave is split along the
-  // vocabulary so that it still fills every CTA pair.
-  pl->n_full_rb = (pl->n_row_blocks / pairs_hw) * pairs_hw;
-  const int tail_rb = pl->n_row_blocks - pl->n_full_rb;
-  int best_s = 1;
-  double best_cost = 1e30;
-  const int max_s = std::max(1, std::min(pl->tiles_total, 16));
-  for (int s = 1; s <= max_s && tail_rb > 0; ++s) {
-    const int tpc = (pl->tiles_total + s - 1) / s;
-    if ((pl->tiles_total + tpc - 1) / tpc != s) continue;            // every chunk must be non-empty
-    const long long items = (long long)tail_rb * s;
-    const long long waves = (items + pairs_hw - 1) / pairs_hw;
-    const double cost = (double)waves * tpc / pl->tiles_total + 0.01 * (s - 1);   // tail time in full sweeps
-    if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s; }
+  // The (row block, tile) space is cut into one contiguous range per CTA pair (scd::NameWork): every pair gets the same
+  // number of tiles (+-1) whatever N is, and starts as few work items as possible.  (Round 1 gave whole row blocks to
+  // whole waves and cut only the tail wave along the vocabulary: at 63 row blocks on 74 pairs that made six 14-tile
+  // items per pair, each paying the item start-up and the final exact scan.)
+  pl->n_pairs = (int)std::max<long long>(1, std::min<long long>(pairs_hw, pl->work_total));
+  const scd::NameWork w{pl->work_total, pl->tiles_total, pl->n_pairs};
+  int slots = 1;
+  if (pl->work_total % pl->n_pairs != 0 || (pl->work_total / pl->n_pairs) % pl->tiles_total != 0) {
+    // a pair boundary falls inside some row block: bound the pieces by ceil(T / smallest range) + 1, then tighten by
+    // walking the boundaries (n_pairs of them)
+    slots = 0;
+    int cur_rb = -1, cur = 0;
+    for (int q = 0; q < pl->n_pairs; ++q) {
+      const long long lo = w.bound(q), hi = w.bound(q + 1);
+      if (lo >= hi) continue;
+      const int rb_first = (int)(lo / pl->tiles_total), rb_last = (int)((hi - 1) / pl->tiles_total);
+      if (rb_first == cur_rb) ++cur; else { cur_rb = rb_first; cur = 1; }
+      slots = std::max(slots, cur);
+      if (rb_last != rb_first) { cur_rb = rb_last; cur = 1; }
+    }
+    slots = std::max(slots, 1);
   }
-  pl->n_vsplit = std::max(1, best_s);
-  pl->tiles_per_chunk = std::max(1, (pl->tiles_total + pl->n_vsplit - 1) / pl->n_vsplit);
-  const long long items = pl->n_full_rb + (long long)tail_rb * pl->n_vsplit;
-  pl->n_pairs = (int)std::max<long long>(1, std::min<long long>(pairs_hw, items));
+  pl->n_slots = slots;
   size_t o = 0;
-  const size_t slots = (size_t)pl->n_vsplit * scd::kEpiHalves * (size_t)N;      // one partial list per (chunk, column half)
-  pl->off_val = o; o = align_up(o + slots * pl->kt * sizeof(float), 256);
-  pl->off_idx = o; pl->idx_bytes = slots * pl->kt * sizeof(int); o = align_up(o + pl->idx_bytes, 256);
-  pl->off_max = o; o = align_up(o + slots * sizeof(float), 256);
-  pl->off_sum = o; o = align_up(o + slots * sizeof(float), 256);
+  const size_t lists = (size_t)pl->n_slots * scd::kEpiHalves * (size_t)N;      // one partial list per (piece, column half)
+  pl->off_val = o; o = align_up(o + lists * pl->kt * sizeof(float), 256);
+  pl->off_idx = o; o = align_up(o + lists * pl->kt * sizeof(int), 256);
+  pl->off_max = o; o = align_up(o + lists * sizeof(float), 256);
+  pl->off_sum = o; o = align_up(o + lists * sizeof(float), 256);
   pl->off_scratch = o; o = align_up(o + (size_t)2 * pairs_hw * scd::kEpiHalves * scd::kBlockM * pl->kt * 32 * sizeof(float), 256);
   pl->bytes = std::max<size_t>(o, 256);
   return true;
@@ -236,6 +241,19 @@ int launch_vote(const IdxT* topk_idx, long long idx_stride, int k_used, int64_t 
       topk_idx, idx_stride, k_used, order, offsets, K, reinterpret_cast<const long long*>(excluded), n_excluded, M,
       reinterpret_cast<long long*>(out_names), out_counts, out_distinct, overflow, reinterpret_cast<int*>(spill));
   SCD_LAUNCH_CHECK("vote_kernel");
+  return 0;
+}
+
+int make_peer_ptrs(scd::PeerPtrs* pp, void* const* bufs, void* const* flags, int world, int rank, const char* who) {
+  if (world < 2 || world > scd::kPeerMaxWorld || rank < 0 || rank >= world) return fail("%s: bad world / rank (%d / %d)", who, world, rank);
+  if (!bufs) return fail("%s: null peer buffer table", who);
+  for (int r = 0; r < scd::kPeerMaxWorld; ++r) {
+    pp->buf[r] = r < world ? bufs[r] : nullptr;
+    pp->flags[r] = (r < world && flags) ? reinterpret_cast<unsigned*>(flags[r]) : nullptr;
+    if (r < world && (!pp->buf[r] || (flags && !pp->flags[r]))) return fail("%s: null peer pointer for rank %d", who, r);
+  }
+  pp->world = world;
+  pp->rank = rank;
   return 0;
 }
 
@@ -524,9 +542,36 @@ size_t scd_name_topk_workspace_bytes(int64_t N, int64_t V, int k) {
 int scd_name_topk_plan(int64_t N, int64_t V, int k, int32_t* out6) {
   NamePlan pl;
   if (!out6 || N <= 0 || V <= 0 || !plan_naming(N, V, k, &pl)) return fail("scd_name_topk_plan: bad arguments");
-  out6[0] = pl.n_row_blocks; out6[1] = pl.tiles_total; out6[2] = pl.n_full_rb;
-  out6[3] = pl.n_vsplit; out6[4] = pl.tiles_per_chunk; out6[5] = pl.n_pairs;
+  const scd::NameWork w{pl.work_total, pl.tiles_total, pl.n_pairs};
+  int most_items = 0;                       // work items the busiest pair starts
+  for (int q = 0; q < pl.n_pairs; ++q) {
+    int items = 0;
+    for (int l = (int)w.bound(q), hi = (int)w.bound(q + 1); l < hi; ++items) l += scd::name_item_at(w, q, l, hi).nt;
+    most_items = std::max(most_items, items);
+  }
+  int most_pieces = 0;                      // what the merge kernel derives per row block must agree with the slot count
+  for (int rb = 0; rb < pl.n_row_blocks; ++rb) most_pieces = std::max(most_pieces, w.pieces(rb));
+  if (most_pieces != pl.n_slots) return fail("scd_name_topk_plan: internal error, %d pieces vs %d slots", most_pieces, pl.n_slots);
+  out6[0] = pl.n_row_blocks; out6[1] = pl.tiles_total; out6[2] = pl.n_pairs; out6[3] = pl.n_slots;
+  out6[4] = (int)(pl.work_total / pl.n_pairs);          // tiles of the least loaded pair (the busiest has at most one more)
+  out6[5] = most_items;
   return 0;
+}
+
+int scd_name_topk_plan_pair(int64_t N, int64_t V, int k, int pair, int32_t* out, int max_items) {
+  NamePlan pl;
+  if (N <= 0 || V <= 0 || !plan_naming(N, V, k, &pl) || pair < 0 || pair >= pl.n_pairs || (max_items > 0 && !out)) {
+    fail("scd_name_topk_plan_pair: bad arguments");
+    return -1;
+  }
+  const scd::NameWork w{pl.work_total, pl.tiles_total, pl.n_pairs};
+  int items = 0;
+  for (int l = (int)w.bound(pair), hi = (int)w.bound(pair + 1); l < hi; ++items) {
+    const scd::NameItem it = scd::name_item_at(w, pair, l, hi);
+    if (items < max_items) { out[4 * items] = it.rb; out[4 * items + 1] = it.t0; out[4 * items + 2] = it.nt; out[4 * items + 3] = it.part; }
+    l += it.nt;
+  }
+  return items;
 }
 
 int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, int64_t V, float scale, int k, int want_softmax,
@@ -553,9 +598,8 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
   scd::NameParams p;
   p.n_rows = N;
   p.v_total = V;
-  p.n_full_rb = pl.n_full_rb;
-  p.n_vsplit = pl.n_vsplit;
-  p.tiles_per_chunk = pl.tiles_per_chunk;
+  p.work_total = pl.work_total;
+  p.tiles_total = pl.tiles_total;
   p.n_row_blocks = pl.n_row_blocks;
   p.num_kb = (D + scd::kAKBlock - 1) / scd::kAKBlock;
   p.want_softmax = (want_softmax || row_max || row_sumexp) ? 1 : 0;     // running max / sum-exp needed
@@ -568,8 +612,6 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
   p.prof = g_name_prof;
   p.x = reinterpret_cast<const __nv_bfloat16*>(X);
   p.d = D;
-  if (pl.n_vsplit > 1) SCD_CUDA(cudaMemsetAsync(p.part_idx, 0xFF, pl.idx_bytes, st));   // -1: "row has nothing in this part"
-
   int e = 0;
   if (pl.kt == 1) e = launch_name_topk<1>(mx, mw, p, pl.n_pairs, st);
   else if (pl.kt == 5) e = launch_name_topk<5>(mx, mw, p, pl.n_pairs, st);
@@ -578,8 +620,9 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
 
   const bool stats = want_softmax || row_max || row_sumexp;
   scd::topk_merge_kernel<int, false><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(
-      p.part_val, p.part_idx, stats ? p.part_max : nullptr, stats ? p.part_sum : nullptr, pl.n_vsplit * scd::kEpiHalves, N, pl.kt, k, scale,
-      want_softmax ? 1 : 0, idx_offset, vals, reinterpret_cast<long long*>(idx), row_max, row_sumexp);
+      p.part_val, p.part_idx, stats ? p.part_max : nullptr, stats ? p.part_sum : nullptr, pl.n_slots * scd::kEpiHalves, N, pl.kt, k, scale,
+      want_softmax ? 1 : 0, idx_offset, vals, reinterpret_cast<long long*>(idx), row_max, row_sumexp,
+      scd::NameWork{pl.work_total, pl.tiles_total, pl.n_pairs});
   SCD_LAUNCH_CHECK("topk_merge_kernel");
   return 0;
 }
@@ -592,7 +635,8 @@ int scd_topk_merge(const float* part_vals, const int64_t* part_idx, const float*
   if (want_softmax && (!part_max || !part_sum)) return fail("scd_topk_merge: softmax needs per-part row_max / row_sumexp");
   scd::topk_merge_kernel<long long, true><<<(unsigned)((N + 127) / 128), 128, 0, as_stream(stream)>>>(
       part_vals, reinterpret_cast<const long long*>(part_idx), want_softmax ? part_max : nullptr, want_softmax ? part_sum : nullptr,
-      parts, N, k, k, scale, want_softmax ? 1 : 0, 0, vals, reinterpret_cast<long long*>(idx), nullptr, nullptr);
+      parts, N, k, k, scale, want_softmax ? 1 : 0, 0, vals, reinterpret_cast<long long*>(idx), nullptr, nullptr,
+      scd::NameWork{0, 1, 0});
   SCD_LAUNCH_CHECK("topk_merge_kernel<shards>");
   return 0;
 }
@@ -662,6 +706,62 @@ int scd_vote_records(const int32_t* rec, int k_used, int64_t N, int K, const int
   if (int e = sort_rows_by_label<int>(rec, stride, N, K, out_rows, w, nullptr, 0, st)) return e;
   return launch_vote<int>(rec + 1, stride, k_used, N, w.order, w.offsets, K, excluded, n_excluded, M, out_names, out_counts, out_distinct,
                           overflow, spill, spill_bytes, st);
+}
+
+// ============================================================================ peer-memory exchange
+size_t scd_peer_flag_bytes(void) { return sizeof(unsigned) * scd::kPeerFlagWords; }
+
+size_t scd_peer_mstep_bytes(int K, int D) { return K > 0 && D > 0 ? sizeof(float) * scd::peer_mstep_words(K, D) : 0; }
+
+int scd_peer_barrier(void* const* peer_flags, int world, int rank, int channel, scd_stream_t stream) {
+  scd::PeerPtrs pp;
+  if (channel < 0 || channel >= scd::kPeerChannels) return fail("scd_peer_barrier: bad channel %d", channel);
+  if (int e = make_peer_ptrs(&pp, peer_flags, peer_flags, world, rank, "scd_peer_barrier")) return e;
+  scd::peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(pp, channel);
+  SCD_LAUNCH_CHECK("peer_barrier_kernel");
+  return 0;
+}
+
+int scd_finalize_centers_peer(void* const* peer_bufs, void* const* peer_flags, int world, int rank, int channel,
+                              size_t buf_byte_offset, const float* C_old, float* C_new, float* move_norms, float* counts_out,
+                              double* inertia_out, int K, int D, void* estep_ws, size_t estep_ws_bytes, scd_stream_t stream) {
+  if (K <= 0 || D <= 0) return fail("scd_finalize_centers_peer: bad shape");
+  if (channel < 0 || channel >= scd::kPeerChannels) return fail("scd_finalize_centers_peer: bad channel %d", channel);
+  if (!C_new || !peer_flags) return fail("scd_finalize_centers_peer: null pointer");
+  if (buf_byte_offset % 16 != 0) return fail("scd_finalize_centers_peer: buffer offset must be a multiple of 16 bytes");
+  if (move_norms && !C_old) return fail("scd_finalize_centers_peer: move norms need C_old");
+  if (estep_ws && estep_ws_bytes < scd_estep_workspace_bytes(K, D)) return fail("scd_finalize_centers_peer: estep workspace too small");
+  scd::PeerPtrs pp;
+  if (int e = make_peer_ptrs(&pp, peer_bufs, peer_flags, world, rank, "scd_finalize_centers_peer")) return e;
+  __nv_bfloat16 *chi = nullptr, *clo = nullptr;
+  float* cnorm = nullptr;
+  if (estep_ws) {                       // same carving as scd_estep
+    uint8_t* w8 = reinterpret_cast<uint8_t*>(estep_ws);
+    const size_t plane = align_up((size_t)K * D * 2, 256);
+    chi = reinterpret_cast<__nv_bfloat16*>(w8);
+    clo = reinterpret_cast<__nv_bfloat16*>(w8 + plane);
+    cnorm = reinterpret_cast<float*>(w8 + 2 * plane);
+  }
+  scd::finalize_centers_peer_kernel<<<K, 256, 0, as_stream(stream)>>>(pp, channel, buf_byte_offset / sizeof(float), C_old, C_new,
+                                                                      move_norms, counts_out, inertia_out, K, D, chi, clo, cnorm);
+  SCD_LAUNCH_CHECK("finalize_centers_peer_kernel");
+  return 0;
+}
+
+int scd_pack_vote_records_peer(void* const* peer_bufs, int world, int rank, size_t buf_byte_offset, const int64_t* labels,
+                               const int64_t* topk_idx, int k_total, int k_used, int64_t n, int64_t row_offset, scd_stream_t stream) {
+  if (n < 0 || row_offset < 0 || k_total <= 0 || k_used <= 0 || k_used > k_total) return fail("scd_pack_vote_records_peer: bad arguments");
+  if (buf_byte_offset % 4 != 0) return fail("scd_pack_vote_records_peer: buffer offset must be a multiple of 4 bytes");
+  scd::PeerPtrs pp;
+  if (int e = make_peer_ptrs(&pp, peer_bufs, nullptr, world, rank, "scd_pack_vote_records_peer")) return e;
+  if (n == 0) return 0;
+  if (!labels || !topk_idx) return fail("scd_pack_vote_records_peer: null pointer");
+  const long long total = n * (1 + k_used);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  scd::pack_vote_records_peer_kernel<<<blocks, 256, 0, as_stream(stream)>>>(pp, buf_byte_offset, reinterpret_cast<const long long*>(labels),
+                                                                            reinterpret_cast<const long long*>(topk_idx), k_total, k_used, n, row_offset);
+  SCD_LAUNCH_CHECK("pack_vote_records_peer_kernel");
+  return 0;
 }
 
 int scd_contingency(const void* y_pred, int pred_is_f64, const void* y_true, int true_is_f64, int64_t N, int D,

@@ -59,24 +59,40 @@ vote_kernel(const IdxT* __restrict__ topk_idx, long long idx_stride, int k_used,
   if (threadIdx.x == 0) { n_distinct = 0; n_cand = 0; c_star = 1; chosen_key = ~0ull; }
   __syncthreads();
 
-  for (long long e = threadIdx.x; e < n_entries; e += blockDim.x) {
-    const int row = order[p0 + (int)(e / k_used)];
-    const int j = (int)(e % k_used);
-    const long long name64 = (long long)topk_idx[(long long)row * idx_stride + j];
-    if (name64 < 0) continue;
-    bool skip = false;
-    for (int x = 0; x < n_excluded; ++x) skip |= (excluded[x] == name64);
-    if (skip) continue;
-    const int name = (int)name64;
-    const unsigned first = (unsigned)row * (unsigned)k_used + (unsigned)j;
-    unsigned h = (unsigned)(((unsigned long long)((unsigned)name * 2654435761u) * nslots) >> 32);
-    unsigned probes = 0;
-    while (true) {
-      const int prev = atomicCAS(&keys[h], -1, name);
-      if (prev == -1) atomicAdd(&n_distinct, 1);
-      if (prev == -1 || prev == name) { atomicAdd(&cnts[h], 1); atomicMin(&firsts[h], first); break; }
-      if (++h == nslots) h = 0;
-      if (++probes >= nslots) { atomicExch(overflow_flag, 1); break; }       // only without a spill buffer
+  // Entries are gathered kVoteBatch at a time: the row ids of a batch are loaded first, then all its names (independent
+  // loads, two round trips per batch) and only then inserted.  One entry per trip - load the row id, then its name, then
+  // probe - left a thread of the 6 k-entry clusters of C2 waiting on ~25 dependent memory round trips (42 us per launch).
+  constexpr int kVoteBatch = 8;
+  const int n_ent = (int)n_entries;              // N * k_used < 2^31 (checked by the host)
+  for (int base = 0; base < n_ent; base += kVoteBatch * (int)blockDim.x) {
+    int row[kVoteBatch], jj[kVoteBatch];
+    long long name64[kVoteBatch];
+#pragma unroll
+    for (int u = 0; u < kVoteBatch; ++u) {
+      const int e = base + u * (int)blockDim.x + (int)threadIdx.x;
+      row[u] = -1;
+      if (e < n_ent) { const int r = e / k_used; jj[u] = e - r * k_used; row[u] = order[p0 + r]; }
+    }
+#pragma unroll
+    for (int u = 0; u < kVoteBatch; ++u)
+      name64[u] = row[u] >= 0 ? (long long)topk_idx[(long long)row[u] * idx_stride + jj[u]] : -1;
+#pragma unroll
+    for (int u = 0; u < kVoteBatch; ++u) {
+      if (name64[u] < 0) continue;
+      bool skip = false;
+      for (int x = 0; x < n_excluded; ++x) skip |= (excluded[x] == name64[u]);
+      if (skip) continue;
+      const int name = (int)name64[u];
+      const unsigned first = (unsigned)row[u] * (unsigned)k_used + (unsigned)jj[u];
+      unsigned h = (unsigned)(((unsigned long long)((unsigned)name * 2654435761u) * nslots) >> 32);
+      unsigned probes = 0;
+      while (true) {
+        const int prev = atomicCAS(&keys[h], -1, name);
+        if (prev == -1) atomicAdd(&n_distinct, 1);
+        if (prev == -1 || prev == name) { atomicAdd(&cnts[h], 1); atomicMin(&firsts[h], first); break; }
+        if (++h == nslots) h = 0;
+        if (++probes >= nslots) { atomicExch(overflow_flag, 1); break; }       // only without a spill buffer
+      }
     }
   }
   __syncthreads();

@@ -7,8 +7,8 @@ the GPUs, gloo in the CPU tests) for the two exchange steps the path really has:
     the ``[N, k]`` (value, index) lists (+ per-row max / sum-exp when the softmax is wanted) and a k-way
     merge kernel.  Row-sharded naming needs no exchange at all;
   * vote: each rank packs its rows' ``[label, name_0 .. name_(k-1)]`` into int32 records, ONE all-gather
-    (``RowGather``) replicates them and every rank runs the exact vote on the gathered records
-    (``sharded_vote``).  Per-cluster name histograms are sparse and unbounded, so "histograms add" is done
+    (``RowGather``, or the peer-memory stores of ``peer.PeerExchange``) replicates them and every rank runs the
+    exact vote on the gathered records (``sharded_vote``).  Per-cluster name histograms are sparse and unbounded, so "histograms add" is done
     by gathering the 24-byte rows, not K x V dense tables.
 """
 from __future__ import annotations
@@ -136,8 +136,13 @@ def grid_2d(world: int, rank: int, vocab_ways: int):
 def sharded_vote(labels_local: torch.Tensor, idx_local: torch.Tensor, top_k: int, n_clusters: int, num_common: int,
                  gather: 'RowGather', plan=None, known_name_idx=None):
     """Row-sharded vote: pack this rank's records into ``gather.local`` (``RowGather(n_total, (1 + top_k,), int32)``),
-    all-gather once, vote on the gathered records.  Every rank returns the full result of ``naming.vote_device``."""
+    all-gather once, vote on the gathered records.  Every rank returns the full result of ``naming.vote_device``.
+    ``gather`` may also be a ``peer.PeerExchange``: the records are then stored straight into every rank's gathered
+    array over NVLink peer memory (no NCCL launch)."""
     from . import naming
-    naming.pack_vote_records(labels_local, idx_local, top_k, out=gather.local)
-    records = gather.gather()
+    if hasattr(gather, 'gather_records'):          # peer.PeerExchange: the pack kernel's stores are the all-gather
+        records = gather.gather_records(labels_local, idx_local, top_k)
+    else:
+        naming.pack_vote_records(labels_local, idx_local, top_k, out=gather.local)
+        records = gather.gather()
     return naming.vote_records(records, n_clusters, num_common, known_name_idx=known_name_idx, plan=plan)

@@ -81,23 +81,35 @@ def _estep(X, C, labels_out, inertia_acc, mindist=None, exact=False):
 class _MStep:
     """Workspace + launches of the M-step for a fixed (N, D, K)."""
 
-    def __init__(self, n, d, k, device):
+    def __init__(self, n, d, k, device, ws=None):
         lib = _lib.load()
         self.n, self.d, self.k = n, d, k
-        self.ws = torch.zeros(lib.scd_mstep_workspace_bytes(n, k), dtype=torch.uint8, device=device)
+        self.ws = ws if ws is not None else torch.zeros(lib.scd_mstep_workspace_bytes(n, k), dtype=torch.uint8, device=device)
         # one buffer [K*D sums | K counts | inertia] (fp32) so the row-sharded case all-reduces it in one call
         self.packed = torch.zeros(k * d + k + 1, dtype=torch.float32, device=device)
         self.sums = self.packed[:k * d].view(k, d)
         self.counts_f = self.packed[k * d:k * d + k]
         self.counts = torch.empty(k, dtype=torch.int32, device=device)
+        self.peer = None                                  # (PeerExchange, block) while the sums live in a peer-mapped block
         self.norms = torch.zeros(max(k, 1), dtype=torch.float32, device=device)     # ||c_new[k] - c_old[k]||
         self.shift = torch.zeros(1, dtype=torch.float32, device=device)
         self.tc = bool(lib.scd_estep_uses_tensor_cores(max(n, 1), d, k))
+
+    def bind_peer(self, px, block):
+        """Let the segment sum write straight into this rank's block of a ``peer.PeerExchange`` (sums, counts, inertia)."""
+        self.peer = (px, block)
+        self.sums, self.counts = block[0], block[1]
 
     def sums_counts(self, X, labels):
         lib = _lib.load()
         _lib.check(lib.scd_mstep_sums(X.data_ptr(), labels.data_ptr(), self.n, self.d, self.k, self.sums.data_ptr(),
                                       self.counts.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _stream()), 'scd_mstep_sums')
+
+    def finalize_peer(self, c_old, c_new, inertia_out, estep: '_EStep | None' = None):
+        """The row-sharded M-step's all-reduce + divide in one launch over peer memory (``scd_finalize_centers_peer``);
+        the reduced inertia lands in ``inertia_out``, the reduced counts in ``counts_f``, move norms in ``norms``."""
+        px, block = self.peer
+        px.finalize(block, c_old, c_new, self.norms, self.counts_f, inertia_out, estep)
 
     def finalize(self, c_old, c_new, counts_f=None, estep: '_EStep | None' = None, shift=True):
         """divide (+ per-cluster move norms when ``c_old`` is given; ``shift=True`` also sums them on the device into
@@ -212,6 +224,26 @@ class K_Means:
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.process_group)
         return out
 
+    def _peer_exchange(self, k, d, device):
+        """The NVLink peer-memory exchange of this fit's (K, D), or None (single rank, a non-NCCL group such as the gloo
+        CPU tests, symmetric memory unavailable, or SCD_B200_EXCHANGE=nccl): then the packed NCCL all-reduce is used."""
+        import os
+        if self.process_group is None or os.environ.get('SCD_B200_EXCHANGE', 'peer') == 'nccl':
+            return None
+        from . import peer
+        cache = self.__dict__.setdefault('_px_cache', {})
+        key = (int(k), int(d))
+        if key not in cache:
+            px = None
+            if peer.available(self.process_group):
+                try:
+                    px = peer.PeerExchange(self.process_group, k, d, device=device)
+                except Exception as e:                         # every rank fails alike (same driver, same allocator)
+                    import warnings
+                    warnings.warn(f'scd_b200: peer-memory exchange unavailable ({e}); using the NCCL all-reduce')
+            cache[key] = px
+        return cache[key]
+
     def _allreduce(self, mstep: _MStep, inertia_acc: torch.Tensor):
         """one packed all-reduce of [K*D sums | K counts | inertia] when rows are sharded."""
         if self.process_group is None:
@@ -242,6 +274,8 @@ class K_Means:
         mstep = _MStep(X_all.shape[0], d, k, dev)
         estep = _EStep(k, d, dev)
         inertia_acc = torch.zeros(1, dtype=torch.float64, device=dev)
+        px = self._peer_exchange(k, d, dev)
+        inertia_red = torch.zeros(1, dtype=torch.float64, device=dev) if px is not None else None
         c_cur = centers.clone().contiguous()
         c_new = torch.empty_like(c_cur)
         # inertia and the K move norms leave the device as two small pinned copies: the one host sync per iteration
@@ -252,6 +286,10 @@ class K_Means:
         u_view = labels[l_num:]
         for it in range(self.max_iterations):
             n_done = it + 1
+            if px is not None:                      # this iteration's [sums | counts | inertia] block, mapped by every rank
+                block = px.next_mstep_block()
+                mstep.bind_peer(px, block)
+                inertia_acc = block[2]
             inertia_acc.zero_()
             if X_assign.shape[0]:
                 self._assign(X_assign, c_cur, u_view, inertia_acc, estep)          # :58-60 / :105-107,:111
@@ -260,9 +298,12 @@ class K_Means:
                 _lib.check(lib.scd_labelled_inertia(l_feats.data_ptr(), labels.data_ptr(), l_num, d, c_cur.data_ptr(), k,
                                                     inertia_acc.data_ptr(), _stream()), 'scd_labelled_inertia')   # :108-110
             mstep.sums_counts(X_all, labels)                                       # :61-64 / :113-116
-            counts_f = self._allreduce(mstep, inertia_acc)
-            mstep.finalize(c_cur, c_new, counts_f, estep=estep if mstep.tc else None, shift=False)   # divide + :71 / :123
-            host_i.copy_(inertia_acc, non_blocking=True)
+            if px is not None:                      # all-reduce over peer loads + divide + :71 / :123, one launch
+                mstep.finalize_peer(c_cur, c_new, inertia_red, estep=estep if mstep.tc else None)
+            else:
+                counts_f = self._allreduce(mstep, inertia_acc)
+                mstep.finalize(c_cur, c_new, counts_f, estep=estep if mstep.tc else None, shift=False)   # divide + :71 / :123
+            host_i.copy_(inertia_red if px is not None else inertia_acc, non_blocking=True)
             host_n.copy_(mstep.norms, non_blocking=True)
             torch.cuda.current_stream().synchronize()                              # the one host sync per iteration
             inertia = float(host_i[0])

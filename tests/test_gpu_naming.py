@@ -186,8 +186,10 @@ def test_full_size_c2_properties():
 
 @pytest.mark.parametrize('softmax', [False, True])
 def test_host_features_stream_in_chunks_and_equal_the_resident_launch(softmax):
-    """score_topk on HOST features uploads wave-sized chunks under the kernel; rows are independent, so the result
-    must equal the single resident launch bit for bit (incl. the ragged last chunk)."""
+    """score_topk on HOST features uploads wave-sized chunks under the kernel; rows are independent, so indices and
+    logits must equal the single resident launch bit for bit (incl. the ragged last chunk).  The softmax denominator
+    is summed per piece of the vocabulary sweep, and where a sweep is cut depends on the rows of the launch: the
+    probabilities agree to fp32 rounding."""
     n, d, v = 2 * naming.STREAM_ROWS + 1111, 256, 3000
     g = torch.Generator().manual_seed(77)
     feats = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1)
@@ -196,7 +198,8 @@ def test_host_features_stream_in_chunks_and_equal_the_resident_launch(softmax):
     v_res, i_res = naming.score_topk(feats.cuda(), vocab, k=5, softmax=softmax)
     for host in (feats, feats.pin_memory(), feats.numpy()):
         v_str, i_str = naming.score_topk(host, vocab, k=5, softmax=softmax)
-        assert torch.equal(i_str, i_res) and torch.equal(v_str, v_res)
+        assert torch.equal(i_str, i_res)
+        assert torch.allclose(v_str, v_res, rtol=2e-6, atol=0) if softmax else torch.equal(v_str, v_res)
 
 
 @pytest.mark.parametrize('n,v,d,k', [(40000, 11000, 64, 5), (40000, 300, 64, 1), (60000, 500, 40, 5), (40000, 5000, 512, 5),

@@ -1,0 +1,123 @@
+"""Two ranks on two GPUs (skipped on a single-GPU box): the exchange steps over NVLink peer memory - the fused
+all-reduce + divide of the M-step (scd_finalize_centers_peer) and the vote records stored into every rank
+(scd_pack_vote_records_peer + scd_peer_barrier) - against the NCCL path and against the single-rank result."""
+import os
+import socket
+import traceback
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, errq):
+    try:
+        import datetime
+        import torch.distributed as dist
+        os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+        torch.cuda.set_device(rank)
+        dist.init_process_group('nccl', rank=rank, world_size=world, timeout=datetime.timedelta(seconds=180),
+                                device_id=torch.device('cuda', rank))
+        from scd_b200 import dist as sdist, kmeans, naming, peer, synth
+        group = dist.group.WORLD
+        assert peer.available(group)
+        cfg = synth.Config('peer', 9002, 24, 3000, 5)
+        data = synth.make(cfg, d=256)
+        X, Xc, W = data['X'], data['Xc'], data['W']
+        lo, hi = sdist.shard_bounds(cfg.n, world, rank)
+        Xs = X[lo:hi].cuda()
+
+        # ---- fit over peer memory == fit over NCCL (same reduction order for G = 2) == single-rank fit within rounding
+        one = kmeans.K_Means(k=cfg.k, max_iterations=6, n_init=1, init='random', random_state=7)
+        one.fit(X.cuda())
+        fits = {}
+        for ex in ('peer', 'nccl'):
+            os.environ['SCD_B200_EXCHANGE'] = ex
+            sh = kmeans.K_Means(k=cfg.k, max_iterations=6, n_init=2, init='random', random_state=7, process_group=group)
+            sh.fit(Xs)
+            assert (sh._peer_exchange(cfg.k, 256, Xs.device) is not None) == (ex == 'peer')
+            fits[ex] = sh
+            both = [torch.empty_like(sh.cluster_centers_) for _ in range(world)]
+            dist.all_gather(both, sh.cluster_centers_.contiguous())
+            assert torch.equal(both[0].view(torch.int32), both[1].view(torch.int32)), f'{ex}: centres differ between the ranks'
+            assert sh.n_iter_ == one.n_iter_
+            assert torch.allclose(sh.cluster_centers_, one.cluster_centers_, atol=1e-5, rtol=1e-5, equal_nan=True)
+            assert (sh.labels_ == one.labels_[lo:hi]).float().mean().item() > 0.999
+            assert abs(float(sh.inertia_) - float(one.inertia_)) < 1e-4 * max(1.0, float(one.inertia_))
+        os.environ['SCD_B200_EXCHANGE'] = 'peer'
+        assert torch.allclose(fits['peer'].cluster_centers_, fits['nccl'].cluster_centers_, atol=1e-6, rtol=1e-6, equal_nan=True)
+        assert torch.equal(fits['peer'].labels_, fits['nccl'].labels_)
+
+        # ---- fit_mix (labelled rows replicated, counted once) and k-means++ with random_state=None over peer memory
+        y = data['y']
+        lab_mask = y < 6
+        L, lt = X[lab_mask][:300], y[lab_mask][:300]
+        U = X[~lab_mask]
+        ulo, uhi = sdist.shard_bounds(len(U), world, rank)
+        one = kmeans.K_Means(k=6, max_iterations=5, n_init=1, random_state=1)
+        one.fit_mix(U.cuda(), L.cuda(), lt.cuda())
+        sh = kmeans.K_Means(k=6, max_iterations=5, n_init=1, random_state=1, process_group=group)
+        sh.fit_mix(U[ulo:uhi].cuda(), L.cuda(), lt.cuda())
+        assert torch.allclose(sh.cluster_centers_, one.cluster_centers_, atol=1e-5, rtol=1e-5)
+        assert sh.n_iter_ == one.n_iter_ == len(lt)
+        sh = kmeans.K_Means(k=12, max_iterations=4, n_init=2, random_state=None, process_group=group)
+        sh.fit_mix(U[ulo:uhi].cuda(), L.cuda(), lt.cuda())
+        both = [torch.empty_like(sh.cluster_centers_) for _ in range(world)]
+        dist.all_gather(both, sh.cluster_centers_.contiguous())
+        assert torch.equal(both[0].view(torch.int32), both[1].view(torch.int32))
+
+        # ---- the row-sharded round: records pushed over peer memory, vote == the single-rank vote, several rounds
+        # back to back (double-buffered record arrays, device-side epochs)
+        C0 = data['C0'].cuda()
+        lab1 = torch.empty(cfg.n, dtype=torch.int64, device='cuda')
+        kmeans._estep(X.cuda(), C0, lab1, None)
+        vocab = naming.Vocabulary(W.cuda())
+        _, idx1 = naming.score_topk(Xc, vocab, k=5)
+        names1, counts1, distinct1, rows1, _ = naming.vote_device(idx1, lab1, cfg.k, 5, 20)
+        names1, counts1, distinct1, rows1 = names1.clone(), counts1.clone(), distinct1.clone(), rows1.clone()
+        lab_s, idx_s = lab1[lo:hi].contiguous(), idx1[lo:hi].contiguous()
+        px = peer.PeerExchange(group, cfg.k, 256, n_total=cfg.n, k_used=5)
+        for rnd in range(5):
+            names, counts, distinct, rows, ovf = sdist.sharded_vote(lab_s, idx_s, 5, cfg.k, 20, px)
+            assert int(ovf.item()) == 0
+            assert torch.equal(names, names1) and torch.equal(counts, counts1) and torch.equal(distinct, distinct1) and torch.equal(rows, rows1)
+            rec = px._records[px._rec_parity ^ 1][0][:cfg.n]
+            assert torch.equal(rec[:, 0].long(), lab1) and torch.equal(rec[:, 1:].long(), idx1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
+    except Exception:
+        errq.put(f'rank {rank}:\n{traceback.format_exc()}')
+        raise
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (gpurun --gpus 2)')
+def test_peer_exchange_on_two_gpus():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    errq = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, errq)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(570)
+    msgs = []
+    while not errq.empty():
+        msgs.append(errq.get())
+    alive = [p for p in procs if p.is_alive()]
+    for p in alive:
+        p.kill()
+    assert not msgs, '\n'.join(msgs)
+    assert not alive, 'a rank did not finish'
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]

@@ -152,12 +152,12 @@ def test_c1_full_round_against_the_oracle():
 
 @pytest.mark.parametrize('v,n', [(82_000, 74 * 256 * 4 + 13 * 256 + 5), (100_000, 74 * 256 * 2 + 60 * 256 + 255)])
 def test_scoring_big_vocabulary_multi_wave(v, n):
-    """several whole waves of row blocks + a tail wave that is split along the vocabulary (int32 ranges, big gathers)"""
+    """many row blocks per CTA pair, most swept whole and some cut between two pairs (int32 ranges, big gathers)"""
     g = torch.Generator().manual_seed(v)
     plan = np.zeros(6, dtype=np.int32)
     from scd_b200 import _lib
     _lib.check(_lib.load().scd_name_topk_plan(n, v, 5, plan.ctypes.data), 'plan')
-    assert plan[2] >= 2 * 74 and plan[3] > 1                 # whole-vocabulary items AND a split tail
+    assert plan[0] >= 2 * plan[2] and plan[3] == 2           # whole-vocabulary items AND row blocks cut between two pairs
     feats = torch.empty(n, 768)
     for lo in range(0, n, 65536):
         hi = min(lo + 65536, n)

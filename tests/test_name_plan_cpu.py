@@ -1,6 +1,8 @@
-"""CPU only: invariants of the work partition of the fused scoring/top-k launch (scd_name_topk_plan) - whole waves of
-256-row blocks sweep the vocabulary in one item, the tail wave is cut into non-empty vocabulary chunks that cover every
-tile once, and the cut never costs more than not cutting.  Without a GPU the planner assumes 148 SMs (74 CTA pairs)."""
+"""CPU only: invariants of the work partition of the fused scoring/top-k launch (scd_name_topk_plan / _plan_pair): the
+(256-row block, 224-name tile) space is cut into one contiguous range per CTA pair; every tile is covered exactly once,
+pair loads differ by at most one tile, the pieces of a row block are numbered 0, 1, .. in pair order (= the partial-list
+slots the merge reads) and never exceed the slot count the workspace is sized for.  Without a GPU the planner assumes
+148 SMs (74 CTA pairs)."""
 import numpy as np
 import pytest
 
@@ -13,34 +15,57 @@ TILE = 224
 def _plan(n, v, k=5):
     out = np.zeros(6, dtype=np.int32)
     assert _lib.load().scd_name_topk_plan(n, v, k, out.ctypes.data) == 0
-    return dict(zip(('row_blocks', 'tiles', 'full_rb', 'vsplit', 'tiles_per_chunk', 'pairs'), (int(x) for x in out)))
+    return dict(zip(('row_blocks', 'tiles', 'pairs', 'slots', 'min_tiles', 'most_items'), (int(x) for x in out)))
+
+
+def _items(n, v, pair, k=5):
+    out = np.zeros((4096, 4), dtype=np.int32)
+    cnt = _lib.load().scd_name_topk_plan_pair(n, v, k, pair, out.ctypes.data, 4096)
+    assert 0 <= cnt <= 4096
+    return out[:cnt]
 
 
 @pytest.mark.parametrize('n', [1, 255, 256, 257, 18944, 18945, 15875, 31750, 63500, 127000, 1280000])
 @pytest.mark.parametrize('v', [1, 100, 224, 225, 11000, 21000, 82000, 100000])
 def test_partition_invariants(n, v):
     p = _plan(n, v)
-    assert p['row_blocks'] == -(-n // 256) and p['tiles'] == -(-v // TILE)
-    assert p['full_rb'] % PAIRS == 0 and 0 <= p['row_blocks'] - p['full_rb'] < PAIRS
-    tail = p['row_blocks'] - p['full_rb']
-    s, tpc = p['vsplit'], p['tiles_per_chunk']
-    assert 1 <= s <= 16 and tpc >= 1
-    if tail:
-        assert (s - 1) * tpc < p['tiles'] <= s * tpc              # every chunk non-empty, all tiles covered once
-        waves = -(-tail * s // PAIRS)
-        assert waves * tpc <= -(-tail // PAIRS) * p['tiles'] + 1e-9 or s == 1       # never worse than one chunk
-    else:
-        assert s == 1
-    items = p['full_rb'] + tail * s
-    assert p['pairs'] == min(PAIRS, max(1, items))
+    R, T = -(-n // 256), -(-v // TILE)
+    assert p['row_blocks'] == R and p['tiles'] == T
+    assert p['pairs'] == min(PAIRS, R * T)
+    assert p['min_tiles'] == (R * T) // p['pairs']
+    covered = np.zeros(R * T, dtype=np.int32) if R * T <= 400000 else None
+    pieces_seen = {}
+    total, most = 0, 0
+    for q in range(p['pairs']):
+        items = _items(n, v, q)
+        load = int(items[:, 2].sum())
+        assert p['min_tiles'] <= load <= p['min_tiles'] + 1
+        total += load
+        most = max(most, len(items))
+        for rb, t0, nt, part in items:
+            assert 0 <= rb < R and nt >= 1 and 0 <= t0 and t0 + nt <= T and 0 <= part < p['slots']
+            assert part == pieces_seen.get(int(rb), 0)                 # pieces of a row block: 0, 1, 2 .. in pair order
+            pieces_seen[int(rb)] = int(part) + 1
+            if covered is not None:
+                covered[rb * T + t0: rb * T + t0 + nt] += 1
+        # a pair's range is contiguous: only its first item may start inside a row block, only its last may end inside one
+        for i, (rb, t0, nt, part) in enumerate(items):
+            assert t0 == 0 or i == 0
+            assert t0 + nt == T or i == len(items) - 1
+    assert total == R * T and most == p['most_items']
+    if covered is not None:
+        assert (covered == 1).all()
+    assert max(pieces_seen.values()) == p['slots']
 
 
-def test_the_tail_wave_of_the_bench_workloads_is_cut_where_it_pays():
-    # C2 on one GPU: 496 row blocks = 6 whole waves + 52; at N = 8 ranks the 62 row blocks are one partial wave
-    assert _plan(127000, 21000)['full_rb'] == 444 and _plan(127000, 21000)['vsplit'] > 1
+def test_small_row_shards_start_few_long_items():
+    # C2 at N = 8 ranks: 63 row blocks x 94 tiles on 74 pairs = 80 tiles per pair in at most 2 items (round 1: six 14-tile items)
     p8 = _plan(15875, 21000)
-    assert p8['full_rb'] == 0 and p8['vsplit'] == 7 and p8['tiles_per_chunk'] == 14      # 6 waves x 14 tiles = 0.89 sweeps
-    assert _plan(18944, 21000)['vsplit'] == 1                                             # exactly one whole wave
+    assert p8['min_tiles'] == 80 and p8['most_items'] <= 2 and p8['slots'] <= 3
+    # C2 on one GPU: 497 row blocks -> 631 tiles per pair, 7-8 items, a row block is cut in at most 2 pieces
+    p1 = _plan(127000, 21000)
+    assert p1['min_tiles'] == 631 and p1['most_items'] <= 8 and p1['slots'] == 2
+    assert _plan(18944, 21000)['slots'] == 1                              # exactly one whole row block per pair
 
 
 def test_plan_rejects_bad_arguments():
@@ -49,3 +74,4 @@ def test_plan_rejects_bad_arguments():
     assert lib.scd_name_topk_plan(0, 10, 5, out.ctypes.data) != 0
     assert lib.scd_name_topk_plan(10, 10, 9, out.ctypes.data) != 0
     assert b'scd_name_topk_plan' in lib.scd_last_error()
+    assert lib.scd_name_topk_plan_pair(1000, 1000, 5, 99, out.ctypes.data, 1) == -1

@@ -239,7 +239,7 @@ def step_naming_scale():
         ms = _time(lambda: plan.run(X, vocab, False), reps=5 if n * v > 5e9 else 20)
         pl = np.zeros(6, dtype=np.int32)
         _lib.load().scd_name_topk_plan(n, v, 5, pl.ctypes.data)
-        print(f'rows {n:7d} x vocab {v:6d}: {ms*1e3:9.1f} us  {2*n*v*d/ms/1e9:7.1f} TFLOP/s   plan rb={pl[0]} tiles={pl[1]} full_rb={pl[2]} vsplit={pl[3]} tpc={pl[4]} pairs={pl[5]}')
+        print(f'rows {n:7d} x vocab {v:6d}: {ms*1e3:9.1f} us  {2*n*v*d/ms/1e9:7.1f} TFLOP/s   plan rb={pl[0]} tiles={pl[1]} pairs={pl[2]} slots={pl[3]} tiles_per_pair={pl[4]} items={pl[5]}')
 
 
 def step_small_kernels():
@@ -303,7 +303,7 @@ def step_name_items():
         p = full[:74 * 32].view(74, 32).double()
         pl = np.zeros(6, dtype=np.int32)
         _lib.load().scd_name_topk_plan(n, v, 5, pl.ctypes.data)
-        print(f'=== rows {n} x vocab {v}: {ms*1e3:.1f} us; plan rb={pl[0]} tiles={pl[1]} full_rb={pl[2]} vsplit={pl[3]} tpc={pl[4]}')
+        print(f'=== rows {n} x vocab {v}: {ms*1e3:.1f} us; plan rb={pl[0]} tiles={pl[1]} pairs={pl[2]} slots={pl[3]} tiles_per_pair={pl[4]} items={pl[5]}')
         for k, nm in {0: 'issuer total', 1: 'issuer wait tmem_empty', 2: 'issuer wait a_full', 3: 'issuer wait b_full', 4: 'issuer wait token',
                       5: 'tiles', 8: 'epi total', 9: 'epi wait tmem_full', 10: 'epi item-final scan+write'}.items():
             col = p[:, k]
