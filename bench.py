@@ -346,9 +346,13 @@ class Round:
         self.last = None
 
     # -- one round; `ev_name`: optional (start, stop) events around the scoring/top-k launches
-    def run(self, ev_name=None):
+    PHASES = ('estep', 'mstep_sums', 'reduce_divide', 'scoring_topk', 'record_exchange', 'vote')
+
+    def run(self, ev_name=None, ev_phase=None):
         cfg, nm = self.cfg, self.naming
         launches = 0
+        mark = (lambda i: ev_phase[i].record()) if ev_phase is not None else (lambda i: None)
+        mark(0)
         c_old, c_new = self.C[self.cur], self.C[self.cur ^ 1]
         # ---- k-means iteration: E-step, M-step sums, (all-reduce), divide (+ next E-step's operands)
         inertia = self.inertia
@@ -358,13 +362,16 @@ class Round:
         inertia.zero_()
         ready = self.estep.ready_for == c_old.data_ptr()
         self.estep.run(self.X, c_old, self.labels, inertia); launches += 1 if ready else 2     # (centroid split +) E-step
+        mark(1)
         self.mstep.sums_counts(self.X, self.labels); launches += 3                    # hist+scan, scatter, segment sum
+        mark(2)
         if self.px is not None:                     # all-reduce over peer loads + divide + next E-step operands: one launch
             self.mstep.finalize_peer(c_old, c_new, self.inertia_red, estep=self.estep); launches += 1
         else:
             counts_f = self.km._allreduce(self.mstep, self.inertia)
             launches += 1 if counts_f is not None else 0                              # pack (the all-reduce is NCCL's)
             self.mstep.finalize(c_old, c_new, counts_f, estep=self.estep, shift=False); launches += 1
+        mark(3)
         # ---- full-vocabulary scoring + per-image top-5
         if ev_name is not None:
             ev_name[0].record()
@@ -376,13 +383,23 @@ class Round:
             vals, idx = vals[lo:lo + (self.row_hi - self.row_lo)], idx[lo:lo + (self.row_hi - self.row_lo)]
         if ev_name is not None:
             ev_name[1].record()
+        mark(4)
         # ---- per-cluster vote over all rows
         if self.world == 1:
+            mark(5)
             out = nm.vote_device(idx, None, cfg.k, TOPK, NUM_COMMON, plan=self.vote_plan, presorted=self.mstep); launches += 1
+        elif self.px is not None:
+            records = self.px.gather_records(self.labels, idx, TOPK); launches += 2   # pack kernel = the all-gather, + flag barrier
+            mark(5)
+            out = nm.vote_records(records, cfg.k, NUM_COMMON, plan=self.vote_plan); launches += 3
+            self.records = records
         else:
-            gat = self.px if self.px is not None else self.g_rec
-            out = self.sdist.sharded_vote(self.labels, idx, TOPK, cfg.k, NUM_COMMON, gat, plan=self.vote_plan); launches += 5 if self.px is not None else 4
-            self.records = self.px._records[self.px._rec_parity ^ 1][0][:cfg.n] if self.px is not None else self.g_rec.full
+            nm.pack_vote_records(self.labels, idx, TOPK, out=self.g_rec.local); launches += 1
+            records = self.g_rec.gather()
+            mark(5)
+            out = nm.vote_records(records, cfg.k, NUM_COMMON, plan=self.vote_plan); launches += 3
+            self.records = records
+        mark(6)
         self.cur ^= 1
         self.launches_per_round = launches
         self.last = (vals, idx, out)
@@ -409,19 +426,24 @@ class Round:
                 self.run(); self.run()                       # steady state: the operands of C[0] are in the E-step workspace
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            graphs, events = [], []
+            graphs, events, phase_events = [], [], []
             pool = torch.cuda.graph_pool_handle()
             for _ in range(n_graphs):
                 try:
                     evs = (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
                 except TypeError:
                     evs = None
+                try:
+                    pevs = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(len(self.PHASES) + 1)]
+                except TypeError:
+                    pevs = None
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=side, pool=pool):
-                    self.run(ev_name=evs)
+                    self.run(ev_name=evs, ev_phase=pevs)
                 graphs.append(g)
                 events.append(evs)
-            self.graphs, self.graph_events, self.gstep = graphs, events, 0
+                phase_events.append(pevs)
+            self.graphs, self.graph_events, self.graph_phase_events, self.gstep = graphs, events, phase_events, 0
         except Exception as e:                                  # eager launches are always available
             sys.stderr.write(f'[bench] CUDA graph capture failed, timing eager launches: {e}\n')
             self.graphs = None
@@ -447,6 +469,21 @@ class Round:
             return [self.graph_events[i][0].elapsed_time(self.graph_events[i][1]) for i in sorted(idx)]
         except Exception as e:
             sys.stderr.write(f'[bench] event nodes inside the graphs could not be read ({e}); timing eager launches instead\n')
+            return None
+
+    def graph_phase_us(self, last_n):
+        """Per-phase durations (us, mean over the last `last_n` replays) from the event nodes inside the graphs, or None."""
+        if self.graphs is None or not getattr(self, 'graph_phase_events', None) or self.graph_phase_events[0] is None:
+            return None
+        n = len(self.graphs)
+        try:
+            idx = sorted({(self.gstep - 1 - j) % n for j in range(min(last_n, n, self.gstep))})
+            out = {}
+            for p, name in enumerate(self.PHASES):
+                out[name] = round(float(np.mean([self.graph_phase_events[i][p].elapsed_time(self.graph_phase_events[i][p + 1]) for i in idx])) * 1e3, 1)
+            return out
+        except Exception as e:
+            sys.stderr.write(f'[bench] phase event nodes could not be read ({e})\n')
             return None
 
     def drop_graphs(self):
@@ -506,6 +543,7 @@ def measure(rnd, steps, warmup, world, group, use_graph, sampler=None):
         per_step = [a.elapsed_time(b) for a, b in name_evs]
         where = 'eager rounds right after the timed region'
     name_ms = float(np.mean(per_step))
+    rnd.phase_us = rnd.graph_phase_us(steps) if graphed else None
     t = torch.tensor([ms_total, name_ms], dtype=torch.float64, device='cuda')
     if world > 1:
         import torch.distributed as dist
@@ -568,6 +606,7 @@ def extra_block(name, rank, world, group, peaks, steps, naming_shard, vocab_ways
     blk = dict(workload=f'{cfg.name}: {cfg.n}x{synth.D} image features, K={cfg.k}, V={cfg.v} names, top-{TOPK}, vote top-{NUM_COMMON}',
                sharding=('rows' if rnd.naming_shard == 'rows' else f'{world // rnd.ways} row groups x {rnd.ways} vocabulary shards'),
                ms_per_step=round(ms, 4), naming_ms=round(name_ms, 4), rest_ms=round(ms - name_ms, 4), steps=steps,
+               phases_us_rank0=getattr(rnd, 'phase_us', None),
                kernel_tflops=round(achieved, 1), kernel_frac=round(achieved / peaks['tflops'], 4),
                kernel_frac_of_sustained=round(achieved / peaks['tflops_sustained'], 4),
                launch_mode='cuda-graph replay' if graphed else 'eager', data='synthetic, generated on the device',
@@ -697,6 +736,7 @@ def main():
     ms_per_step, name_ms, graphed = measure(rnd, args.steps, args.warmup, world, group, not args.no_graph, sampler)
     clocks = sampler.result()
     launches_per_round = rnd.launches_per_round
+    phase_us = getattr(rnd, 'phase_us', None)
     rnd.drop_graphs()
     parity = parity_block(rnd, host, world, group)
 
@@ -795,7 +835,7 @@ def main():
                     data='synthetic', config=config, clocks=clocks, e2e=e2e, gpu_launches=launches_per_round * args.steps,
                     launch_mode='cuda-graph replay' if graphed else 'eager',
                     roofline=roofline, cpu_baseline=cpu_baseline, torch_cuda_baseline=torch_base,
-                    split=dict(naming_ms=round(name_ms, 4), rest_ms=round(ms_per_step - name_ms, 4)),
+                    split=dict(naming_ms=round(name_ms, 4), rest_ms=round(ms_per_step - name_ms, 4), phases_us_rank0=phase_us),
                     parity=parity, sustained=sustained, **extra)
         real_stdout.write(json.dumps(line) + '\n')
         real_stdout.flush()

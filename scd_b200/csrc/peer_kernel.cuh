@@ -201,13 +201,14 @@ __global__ void pack_vote_records_peer_kernel(const PeerPtrs pp, size_t buf_byte
                                               const long long* __restrict__ idx, int k_total, int k_used, long long n,
                                               long long row_offset) {
   const int w = 1 + k_used;
-  const long long total = n * w;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const long long i = t / w;
-    const int j = (int)(t - i * w);
-    const int v = j == 0 ? (int)labels[i] : (int)idx[i * k_total + (j - 1)];
-    for (int r = 0; r < pp.world; ++r)
-      reinterpret_cast<int*>(reinterpret_cast<char*>(pp.buf[r]) + buf_byte_offset)[row_offset * w + t] = v;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int v[9];                                        // k_used <= 8
+    v[0] = (int)labels[i];
+    for (int j = 0; j < k_used; ++j) v[1 + j] = (int)idx[i * k_total + j];
+    for (int r = 0; r < pp.world; ++r) {
+      int* dst = reinterpret_cast<int*>(reinterpret_cast<char*>(pp.buf[r]) + buf_byte_offset) + (row_offset + i) * w;
+      for (int j = 0; j < w; ++j) dst[j] = v[j];
+    }
   }
 }
 

@@ -682,8 +682,8 @@ int scd_pack_vote_records(const int64_t* labels, const int64_t* topk_idx, int k_
   if (n < 0 || k_total <= 0 || k_used <= 0 || k_used > k_total) return fail("scd_pack_vote_records: bad arguments");
   if (n == 0) return 0;
   if (!labels || !topk_idx || !rec) return fail("scd_pack_vote_records: null pointer");
-  const long long total = n * (1 + k_used);
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  if (k_used > 8) return fail("scd_pack_vote_records: k_used=%d unsupported (<= 8)", k_used);
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
   scd::pack_vote_records_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(labels),
                                                                        reinterpret_cast<const long long*>(topk_idx), k_total, k_used, n, rec);
   SCD_LAUNCH_CHECK("pack_vote_records_kernel");
@@ -756,8 +756,8 @@ int scd_pack_vote_records_peer(void* const* peer_bufs, int world, int rank, size
   if (int e = make_peer_ptrs(&pp, peer_bufs, nullptr, world, rank, "scd_pack_vote_records_peer")) return e;
   if (n == 0) return 0;
   if (!labels || !topk_idx) return fail("scd_pack_vote_records_peer: null pointer");
-  const long long total = n * (1 + k_used);
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  if (k_used > 8) return fail("scd_pack_vote_records_peer: k_used=%d unsupported (<= 8)", k_used);
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
   scd::pack_vote_records_peer_kernel<<<blocks, 256, 0, as_stream(stream)>>>(pp, buf_byte_offset, reinterpret_cast<const long long*>(labels),
                                                                             reinterpret_cast<const long long*>(topk_idx), k_total, k_used, n, row_offset);
   SCD_LAUNCH_CHECK("pack_vote_records_peer_kernel");

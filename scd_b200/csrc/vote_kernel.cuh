@@ -54,6 +54,8 @@ vote_kernel(const IdxT* __restrict__ topk_idx, long long idx_stride, int k_used,
   int* cnts = keys + nslots;
   unsigned* firsts = reinterpret_cast<unsigned*>(keys + 2ll * nslots);
 
+  const volatile int* vkeys = keys;
+  const volatile unsigned* vfirsts = firsts;
   for (unsigned s = threadIdx.x; s < nslots; s += blockDim.x) { keys[s] = -1; cnts[s] = 0; firsts[s] = 0xFFFFFFFFu; }
   for (int b = threadIdx.x; b < kVoteHistBins; b += blockDim.x) hist[b] = 0;
   if (threadIdx.x == 0) { n_distinct = 0; n_cand = 0; c_star = 1; chosen_key = ~0ull; }
@@ -86,10 +88,21 @@ vote_kernel(const IdxT* __restrict__ topk_idx, long long idx_stride, int k_used,
       const unsigned first = (unsigned)row[u] * (unsigned)k_used + (unsigned)jj[u];
       unsigned h = (unsigned)(((unsigned long long)((unsigned)name * 2654435761u) * nslots) >> 32);
       unsigned probes = 0;
+      // Shared-memory atomics cost ~2 cycles per LANE whatever the address, so they - not the gathers - set the pace of
+      // a 6 k-entry cluster.  The rows of a cluster mostly repeat names that are already in the table: a plain load finds
+      // the slot (no CAS), and the first-position minimum is only attempted when it would lower the stored value.
+      // One atomic per entry (the count) instead of three.
       while (true) {
-        const int prev = atomicCAS(&keys[h], -1, name);
-        if (prev == -1) atomicAdd(&n_distinct, 1);
-        if (prev == -1 || prev == name) { atomicAdd(&cnts[h], 1); atomicMin(&firsts[h], first); break; }
+        int cur = vkeys[h];
+        if (cur == -1) {
+          cur = atomicCAS(&keys[h], -1, name);
+          if (cur == -1) { atomicAdd(&n_distinct, 1); cur = name; }
+        }
+        if (cur == name) {
+          atomicAdd(&cnts[h], 1);
+          if (first < vfirsts[h]) atomicMin(&firsts[h], first);
+          break;
+        }
         if (++h == nslots) h = 0;
         if (++probes >= nslots) { atomicExch(overflow_flag, 1); break; }       // only without a spill buffer
       }
@@ -135,8 +148,12 @@ vote_kernel(const IdxT* __restrict__ topk_idx, long long idx_stride, int k_used,
     return ((unsigned long long)(unsigned)cnts[s] << 32) | (unsigned long long)(0xFFFFFFFFu - firsts[s]);
   };
 
-  if (nc <= 1024) {
-    // ---- one warp: M rounds of "largest (count, earliest first) strictly below the previous pick"
+  if (nc <= 64) {
+    // ---- one warp: M rounds of "largest (count, earliest first) strictly below the previous pick".  Only for short
+    // lists: every round walks the whole list with three dependent shared-memory loads per candidate, and with the
+    // long tie groups real clusters have (hundreds of names seen c* times) a single warp spent 60 k cycles here while
+    // the other fifteen had exited - 80 % of the kernel (ncu source view of round 2a).  Longer lists take the
+    // block-wide rounds below.
     if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
     unsigned long long limit = ~0ull;
@@ -204,10 +221,10 @@ vote_kernel(const IdxT* __restrict__ topk_idx, long long idx_stride, int k_used,
 __global__ void pack_vote_records_kernel(const long long* __restrict__ labels, const long long* __restrict__ idx, int k_total,
                                          int k_used, long long n, int* __restrict__ rec) {
   const int w = 1 + k_used;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n * w; t += (long long)gridDim.x * blockDim.x) {
-    const long long i = t / w;
-    const int j = (int)(t % w);
-    rec[t] = j == 0 ? (int)labels[i] : (int)idx[i * k_total + (j - 1)];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int* dst = rec + i * w;
+    dst[0] = (int)labels[i];
+    for (int j = 0; j < k_used; ++j) dst[1 + j] = (int)idx[i * k_total + j];
   }
 }
 
