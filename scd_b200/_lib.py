@@ -85,3 +85,21 @@ def check(rc: int, what: str) -> None:
 def ptr(t) -> int | None:
     """Device (or host) address of a torch tensor, None for None."""
     return None if t is None else t.data_ptr()
+
+
+_UPLOAD_STREAMS = {}
+
+
+def upload_stream(device=None):
+    """The one side stream per device that host -> device feature uploads are issued on (``naming.score_topk`` and
+    ``kmeans.assign_from_host`` on host inputs).  Staging and destination buffers of those uploads are ALLOCATED under this
+    stream, so an upload never has to wait for the work queued on the caller's stream (the caching allocator hands a
+    block back only to the stream it was allocated on), and successive uploads queue behind each other on the wire."""
+    import torch
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    st = _UPLOAD_STREAMS.get(idx)
+    if st is None:
+        st = _UPLOAD_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return st

@@ -126,6 +126,55 @@ class _MStep:
             estep.ready_for = c_new.data_ptr()
 
 
+PANEL_ROWS = 16384          # rows per upload panel of assign_from_host (50 MB of fp32 at D = 768: ~0.9 ms of PCIe, ~12 us of E-step)
+
+
+def assign_from_host(X_host: torch.Tensor, centers: torch.Tensor, panel_rows: int = PANEL_ROWS):
+    """E-step of one iteration (``faster_mix_k_means_pytorch.py:58-60``) on HOST features: ``torch.from_numpy(x).cuda()``
+    (``main_unsup.py:340``) and the assignment pipelined - the rows go up in panels on a copy stream and each panel is
+    assigned (fused distance + argmin + inertia) while the next one is on the wire, so only the last panel's ~12 us of
+    E-step are left after the transfer.  Rows are independent: labels equal the resident launch bit for bit.
+    Returns ``(X on the device, labels int64 [N], inertia fp64 [1])``."""
+    if not torch.is_tensor(X_host):
+        X_host = torch.from_numpy(np.ascontiguousarray(X_host))
+    if X_host.is_cuda or X_host.dtype != torch.float32 or X_host.dim() != 2:
+        raise ValueError('assign_from_host expects a 2-D float32 host tensor')
+    X_host = X_host.contiguous()
+    Cd = _dev_f32(centers)
+    dev = Cd.device
+    n, d = int(X_host.shape[0]), int(X_host.shape[1])
+    labels = torch.empty(n, dtype=torch.int64, device=dev)
+    inertia = torch.zeros(1, dtype=torch.float64, device=dev)
+    es = _EStep(int(Cd.shape[0]), d, dev)
+    main = torch.cuda.current_stream()
+    copy = _lib.upload_stream(dev)
+    with torch.cuda.stream(copy):                    # allocated under the upload stream: the first panel does not wait for `main`
+        X = torch.empty(n, d, dtype=torch.float32, device=dev)
+    for lo in range(0, n, panel_rows):
+        hi = min(lo + panel_rows, n)
+        with torch.cuda.stream(copy):
+            X[lo:hi].copy_(X_host[lo:hi], non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(copy)
+        main.wait_event(up)
+        if lo:
+            es.ready_for = Cd.data_ptr()             # the centroid planes of the first panel's launch are still in place
+        es.run(X[lo:hi], Cd, labels[lo:hi], inertia)
+    X.record_stream(main)
+    return X, labels, inertia
+
+
+def update_centers(X: torch.Tensor, labels: torch.Tensor, k: int, c_old: torch.Tensor | None = None):
+    """M-step (``faster_mix_k_means_pytorch.py:61-64``): ``centers[j] = mean(X[labels == j])`` on device-resident rows,
+    NaN row for an empty cluster.  Returns ``(centers [K, D], counts int32 [K], per-cluster move norms or None)``."""
+    Xd = _dev_f32(X)
+    ms = _MStep(int(Xd.shape[0]), int(Xd.shape[1]), int(k), Xd.device)
+    ms.sums_counts(Xd, labels)
+    c_new = torch.empty(int(k), int(Xd.shape[1]), dtype=torch.float32, device=Xd.device)
+    ms.finalize(c_old, c_new, shift=False)
+    return c_new, ms.counts, (ms.norms if c_old is not None else None), ms
+
+
 def pairwise_distance(data1, data2, batch_size=None, *, out_device=None):
     """Reference signature (``local_utils/faster_mix_k_means_pytorch.py:177``): squared Euclidean distance
     matrix ``[N, K]``, direct form, fp32.  Like the reference, the result lives on the **CPU** when

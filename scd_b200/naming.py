@@ -170,13 +170,13 @@ def _score_topk_streamed(feats_host: torch.Tensor, vocab: Vocabulary, k: int, so
     vals = torch.empty(n, k, dtype=torch.float32, device=dev)
     idx = torch.empty(n, k, dtype=torch.int64, device=dev)
     main = torch.cuda.current_stream()
-    copy = torch.cuda.Stream()
-    stage = [torch.empty(STREAM_ROWS, d, dtype=torch.float32, device=dev) for _ in range(2)]
+    copy = _lib.upload_stream(dev)
+    with torch.cuda.stream(copy):                    # allocated under the upload stream: chunk 0 does not wait for `main`
+        stage = [torch.empty(STREAM_ROWS, d, dtype=torch.float32, device=dev) for _ in range(2)]
     half = [torch.empty(STREAM_ROWS, d, dtype=torch.bfloat16, device=dev) for _ in range(2)]
     uploaded = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     plans = {}
-    copy.wait_stream(main)
     for c, lo in enumerate(range(0, n, STREAM_ROWS)):
         rows = min(STREAM_ROWS, n - lo)
         b = c & 1
@@ -197,7 +197,7 @@ def _score_topk_streamed(feats_host: torch.Tensor, vocab: Vocabulary, k: int, so
                                      idx[lo:lo + rows].data_ptr(), None, None, ws.data_ptr(), ws.numel(), main.cuda_stream),
                    'scd_name_topk')
     for t in stage:
-        t.record_stream(copy)
+        t.record_stream(main)
     return vals, idx
 
 

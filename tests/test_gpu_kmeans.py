@@ -325,3 +325,24 @@ def test_estep_back_to_back_launches_at_every_ring_layout(k):
     clear = (top2[:, 1] - top2[:, 0]) > 1e-5
     assert torch.equal(lab[:4096][clear], ref[:4096][clear])
     assert int((lab != ref).sum()) <= n // 5000          # near-ties only
+
+
+def test_host_features_are_assigned_in_panels_under_their_upload():
+    """kmeans.assign_from_host (upload in row panels, E-step per panel) equals the resident E-step bit for bit - labels and
+    the device copy of X - and its inertia agrees to fp64 summation order; update_centers equals the M-step of _lloyd."""
+    g = torch.Generator().manual_seed(5)
+    n, d, k = 3 * 4096 + 777, 256, 37
+    X = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1)
+    C = X[torch.randperm(n, generator=g)[:k]].clone()
+    lab_res = torch.empty(n, dtype=torch.int64, device='cuda')
+    inertia_res = torch.zeros(1, dtype=torch.float64, device='cuda')
+    kmeans._estep(X.cuda(), C.cuda(), lab_res, inertia_res)
+    for host in (X, X.pin_memory(), X.numpy()):
+        Xd, lab, inertia = kmeans.assign_from_host(host, C.cuda(), panel_rows=4096)
+        assert torch.equal(Xd.cpu(), X) and torch.equal(lab, lab_res)
+        assert abs(float(inertia) - float(inertia_res)) < 1e-9 * float(inertia_res)
+    centers, counts, norms, _ = kmeans.update_centers(Xd, lab, k, c_old=C.cuda())
+    cen_o = kmeans_oracle.mstep(X, lab.cpu(), C.clone())
+    assert torch.allclose(centers.cpu(), cen_o, atol=1e-5)
+    assert torch.equal(counts.cpu().long(), torch.bincount(lab.cpu(), minlength=k))
+    assert torch.allclose(norms[:k].cpu(), (cen_o - C).norm(dim=1), atol=1e-5)
