@@ -281,7 +281,8 @@ class Round:
     Successive rounds are successive k-means iterations: the centres ping-pong between two buffers and
     scd_finalize_centers leaves the next E-step's operands in place, exactly like K_Means._lloyd."""
 
-    def __init__(self, cfg, rank, world, group, naming_shard='rows', vocab_ways=None, data=None, host_data=None, exchange='peer'):
+    def __init__(self, cfg, rank, world, group, naming_shard='rows', vocab_ways=None, data=None, host_data=None, exchange='peer',
+                 fused_em=False):
         from scd_b200 import dist as sdist, kmeans, naming, synth
         self.cfg, self.rank, self.world, self.group = cfg, rank, world, group
         self.kmeans, self.naming, self.sdist = kmeans, naming, sdist
@@ -301,6 +302,7 @@ class Round:
         self.inertia = torch.zeros(1, dtype=torch.float64, device=dev)
         self.mstep = kmeans._MStep(n_local, d, cfg.k, dev)
         self.estep = kmeans._EStep(cfg.k, d, dev)
+        self.fused_em = fused_em and self.estep.fusable(n_local)
         self.km = kmeans.K_Means(k=cfg.k, process_group=group if world > 1 else None)
         self.labels = torch.empty(n_local, dtype=torch.int64, device=dev)
         # the two exchange steps: NVLink peer memory (the fused kernels of scd_b200/peer.py) unless --exchange nccl
@@ -361,9 +363,13 @@ class Round:
             inertia = self.mstep.peer[1][2]
         inertia.zero_()
         ready = self.estep.ready_for == c_old.data_ptr()
-        self.estep.run(self.X, c_old, self.labels, inertia); launches += 1 if ready else 2     # (centroid split +) E-step
-        mark(1)
-        self.mstep.sums_counts(self.X, self.labels); launches += 3                    # hist+scan, scatter, segment sum
+        if self.fused_em:                           # E-step + M-step sums in ONE pass over X (rows re-read from L2 after the argmin)
+            self.estep.run(self.X, c_old, self.labels, inertia, mstep=self.mstep); launches += 1 if ready else 2
+            mark(1)
+        else:
+            self.estep.run(self.X, c_old, self.labels, inertia); launches += 1 if ready else 2     # (centroid split +) E-step
+            mark(1)
+            self.mstep.sums_counts(self.X, self.labels); launches += 3                # hist+scan, scatter, segment sum
         mark(2)
         if self.px is not None:                     # all-reduce over peer loads + divide + next E-step operands: one launch
             self.mstep.finalize_peer(c_old, c_new, self.inertia_red, estep=self.estep); launches += 1
@@ -387,7 +393,10 @@ class Round:
         # ---- per-cluster vote over all rows
         if self.world == 1:
             mark(5)
-            out = nm.vote_device(idx, None, cfg.k, TOPK, NUM_COMMON, plan=self.vote_plan, presorted=self.mstep); launches += 1
+            if self.fused_em:                       # no label sort was needed for the M-step: the vote does its own
+                out = nm.vote_device(idx, self.labels, cfg.k, TOPK, NUM_COMMON, plan=self.vote_plan); launches += 3
+            else:
+                out = nm.vote_device(idx, None, cfg.k, TOPK, NUM_COMMON, plan=self.vote_plan, presorted=self.mstep); launches += 1
         elif self.px is not None:
             records = self.px.gather_records(self.labels, idx, TOPK); launches += 2   # pack kernel = the all-gather, + flag barrier
             mark(5)
@@ -587,13 +596,13 @@ def parity_block(rnd, data, world, group):
     return out
 
 
-def extra_block(name, rank, world, group, peaks, steps, naming_shard, vocab_ways=None, exchange='peer'):
+def extra_block(name, rank, world, group, peaks, steps, naming_shard, vocab_ways=None, exchange='peer', fused_em=False):
     """Timing + parity of one of the other BASELINE.json configs on the same N GPUs (device-generated inputs)."""
     from scd_b200 import synth
     cfg = synth.CONFIGS[name]
     t0 = time.time()
     data = device_data(cfg, torch.device('cuda'), synth.D)
-    rnd = Round(cfg, rank, world, group, naming_shard, vocab_ways, data=data, exchange=exchange)
+    rnd = Round(cfg, rank, world, group, naming_shard, vocab_ways, data=data, exchange=exchange, fused_em=fused_em)
     if world == 1:
         data_keep = None
     else:
@@ -621,7 +630,8 @@ def e2e_round(cfg, host, vocab, pinned, out_host):
     The PCIe link is the bound (780 MB up), so the round is ordered around it: the CLIP-like features go first (scored
     chunk by chunk under their own upload), their top-k lists leave on a side stream while the k-means features go up in
     panels (each panel assigned while the next is on the wire); M-step, vote and the small results follow the last byte."""
-    from scd_b200 import kmeans, naming
+    from scd_b200 import kmeans, naming, synth
+    synth_d = synth.D
     main = torch.cuda.current_stream()
     C = pinned['C0'].to('cuda', non_blocking=True)
     vals, idx = naming.score_topk(pinned['Xc'], vocab, k=TOPK, softmax=False)       # host features: chunked upload under the kernel
@@ -630,9 +640,12 @@ def e2e_round(cfg, host, vocab, pinned, out_host):
     with torch.cuda.stream(side):
         out_host['vals'].copy_(vals, non_blocking=True)
         out_host['idx'].copy_(idx, non_blocking=True)
-    X, labels, inertia = kmeans.assign_from_host(pinned['X'], C)                    # panels up, E-step per panel
-    centers, counts, _, ms = kmeans.update_centers(X, labels, cfg.k)
-    names, counts_v, distinct, rows, ovf = naming.vote_device(idx, None, cfg.k, TOPK, NUM_COMMON, presorted=ms)
+    ms = kmeans._MStep(cfg.n, synth_d, cfg.k, C.device)
+    fused = False           # one-pass E+M exists (scd_estep_mstep) but its vector reductions cost more than the second pass over X
+    X, labels, inertia = kmeans.assign_from_host(pinned['X'], C, mstep=ms if fused else None)   # panels up, E(+M) per panel
+    centers, counts, _, ms = kmeans.update_centers(X, labels, cfg.k, mstep=ms if fused else None)
+    names, counts_v, distinct, rows, ovf = naming.vote_device(idx, labels if fused else None, cfg.k, TOPK, NUM_COMMON,
+                                                              presorted=None if fused else ms)
     for key, t in (('labels', labels), ('centers', centers), ('names', names), ('counts', counts_v), ('inertia', inertia)):
         out_host[key].copy_(t, non_blocking=True)
     main.wait_stream(side)
@@ -669,6 +682,7 @@ def main():
     ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl'],
                     help='N > 1: the M-step sum and the vote-record replication run over NVLink peer memory inside the kernels '
                          '(scd_b200/peer.py), or as NCCL all-reduce / all-gather launches between them')
+    ap.add_argument('--fused-em', action='store_true', help='k-means iteration as ONE pass over X (scd_estep_mstep: rows re-read from L2 and reduced with red.v4 after the argmin) - measured slower than the two-pass default, DESIGN 3.3')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of CUDA-graph replays')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-torch-baseline', action='store_true')
@@ -739,13 +753,14 @@ def main():
         group = dist.group.WORLD
     peaks = load_peaks()
     host = synth.make(cfg)
-    rnd = Round(cfg, rank, world, group, args.naming_shard, args.vocab_ways or None, host_data=host, exchange=args.exchange)
+    rnd = Round(cfg, rank, world, group, args.naming_shard, args.vocab_ways or None, host_data=host, exchange=args.exchange, fused_em=args.fused_em)
 
     sampler = ClockSampler(physical_gpu_index(local_rank), enabled=not args.no_clocks)
     ms_per_step, name_ms, graphed = measure(rnd, args.steps, args.warmup, world, group, not args.no_graph, sampler)
     clocks = sampler.result()
     launches_per_round = rnd.launches_per_round
     phase_us = getattr(rnd, 'phase_us', None)
+    fused_flag = rnd.fused_em
     rnd.drop_graphs()
     parity = parity_block(rnd, host, world, group)
 
@@ -832,11 +847,11 @@ def main():
     torch.cuda.empty_cache()
     if not args.no_extra:
         try:
-            extra['c5'] = extra_block('C5', rank, world, group, peaks, args.extra_steps, 'rows', exchange=args.exchange)
-            extra['c4_vocab_shard'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'vocab', exchange=args.exchange)
-            extra['c4_rows'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'rows', exchange=args.exchange)
+            extra['c5'] = extra_block('C5', rank, world, group, peaks, args.extra_steps, 'rows', exchange=args.exchange, fused_em=args.fused_em)
+            extra['c4_vocab_shard'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'vocab', exchange=args.exchange, fused_em=args.fused_em)
+            extra['c4_rows'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'rows', exchange=args.exchange, fused_em=args.fused_em)
             if world >= 4:
-                extra['c4_grid_2d'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'vocab', vocab_ways=2, exchange=args.exchange)
+                extra['c4_grid_2d'] = extra_block('C4', rank, world, group, peaks, args.extra_steps, 'vocab', vocab_ways=2, exchange=args.exchange, fused_em=args.fused_em)
         except Exception as e:
             if world > 1:
                 raise                                              # a rank that skips a collective would hang the others
@@ -848,6 +863,7 @@ def main():
                     data='synthetic', config=config, clocks=clocks, e2e=e2e, gpu_launches=launches_per_round * args.steps,
                     launch_mode='cuda-graph replay' if graphed else 'eager',
                     roofline=roofline, cpu_baseline=cpu_baseline, torch_cuda_baseline=torch_base,
+                    kmeans_pass='E-step + M-step sums fused in one pass over X' if fused_flag else 'E-step, label sort, segment sum: two passes over X',
                     split=dict(naming_ms=round(name_ms, 4), rest_ms=round(ms_per_step - name_ms, 4), phases_us_rank0=phase_us),
                     parity=parity, sustained=sustained, **extra)
         real_stdout.write(json.dumps(line) + '\n')

@@ -9,5 +9,5 @@ d=json.load(open('gpurun_out/${TAG}_n1.json'))
 print('value', d['value'], 'split', d['split'])
 print('e2e', d['e2e'])
 PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"vote_kernel" -s 6 -c 1 -o gpurun_out/${TAG}_vote -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-torch-baseline --no-clocks --no-extra --no-graph > gpurun_out/${TAG}_ncu.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"vote_kernel" -s 2 -c 1 -o gpurun_out/${TAG}_vote -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-torch-baseline --no-clocks --no-extra --no-graph > gpurun_out/${TAG}_ncu.log 2>&1
 tail -3 gpurun_out/${TAG}_ncu.log
