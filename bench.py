@@ -44,6 +44,9 @@ import torch
 METRIC = 'ms per naming round (k-means iter + vocab top-k + vote)'
 CPU_SAMPLE_ROWS = int(os.environ.get('SCD_BENCH_CPU_ROWS', '8192'))      # rows of the bounded CPU sample (tests shrink it)
 TOPK, NUM_COMMON = 5, 20
+CPU_KIND_DETAIL = {'reference': "k-means E-step = the reference's own pairwise_distance imported from the checkout; M-step loop, inline "
+                                'scoring/top-k block and vote = the oracle restatement (script code, not importable)',
+                   'port': 'oracle restatement of the reference (the checkout is absent on this box)'}
 
 
 # ------------------------------------------------------------------------------------------ helpers
@@ -138,6 +141,31 @@ def sha(t: torch.Tensor) -> str:
 
 # ------------------------------------------------------------------------------------------ CPU legs
 _CPU_DATA = {}
+_REF_PD = []
+
+
+def reference_pairwise_distance():
+    """The reference's own `pairwise_distance` (local_utils/faster_mix_k_means_pytorch.py:177), imported unmodified when
+    the checkout is present (the build container); None on the GPU box, where the CPU legs run the oracle port.  The
+    inline naming / vote blocks of main_*.py are script code and are always the oracle's restatement."""
+    if not _REF_PD:
+        fn = None
+        ref = os.environ.get('SCD_REFERENCE_DIR', '/root/reference')
+        if os.path.isdir(os.path.join(ref, 'local_utils')):
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location('_scd_ref_kmeans', os.path.join(ref, 'local_utils', 'faster_mix_k_means_pytorch.py'))
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                fn = mod.pairwise_distance
+            except Exception as e:
+                sys.stderr.write(f'[bench] reference checkout present but not importable ({e}); using the oracle port\n')
+        _REF_PD.append(fn)
+    return _REF_PD[0]
+
+
+def cpu_kind():
+    return 'reference' if reference_pairwise_distance() is not None else 'port'
 
 
 def cpu_round_ms(cfg, sample_rows, threads, repeats=2):
@@ -146,6 +174,7 @@ def cpu_round_ms(cfg, sample_rows, threads, repeats=2):
     from oracle import kmeans_oracle, naming_oracle
     from scd_b200 import synth
     torch.set_num_threads(threads)
+    ref_pd = reference_pairwise_distance()
     n = min(sample_rows, cfg.n)
     if (cfg.name, n) not in _CPU_DATA:
         _CPU_DATA[(cfg.name, n)] = synth.make(cfg, n_rows=n)
@@ -154,7 +183,11 @@ def cpu_round_ms(cfg, sample_rows, threads, repeats=2):
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        labels, _, _ = kmeans_oracle.estep(X, C0, 1024)                     # pairwise_distance(X, C, 1024) + torch.min
+        if ref_pd is not None:                                              # the reference's own function, unmodified
+            mind, labels = torch.min(ref_pd(X, C0, 1024), dim=1)           # faster_mix_k_means_pytorch.py:58-59
+            mind.sum()
+        else:
+            labels, _, _ = kmeans_oracle.estep(X, C0, 1024)                 # pairwise_distance(X, C, 1024) + torch.min
         kmeans_oracle.mstep(X, labels, C0.clone())                          # the :61-64 loop
         t1 = time.perf_counter()
         idx, _ = naming_oracle.score_topk(Xc, W, 5, variant='ptsup')        # main_ptsup.py:526-545 restated
@@ -716,7 +749,9 @@ def main():
                f'[rows, k] lists inside a row group + k-way merge); vote records all-gathered once, exact vote replicated')
     config = dict(workload=f'{cfg.name}: {cfg.n}x{synth.D} image features, K={cfg.k}, V={cfg.v} names, top-5, vote top-20',
                   n=cfg.n, d=synth.D, k=cfg.k, v=cfg.v, topk=5,
-                  l2=f'inputs ({feat_mb:.0f} MB features + {voc_mb:.0f} MB vocabulary) exceed the 126 MB L2', parallelism=par)
+                  l2=(f'inputs ({feat_mb:.0f} MB features + {voc_mb:.0f} MB vocabulary) exceed the 126 MB L2' if feat_mb + voc_mb > 126 else
+                      f'inputs ({feat_mb:.0f} MB features + {voc_mb:.0f} MB vocabulary) FIT the 126 MB L2: not a valid timing config, parity only'),
+                  parallelism=par)
 
     # -------------------------------------------------------------------------------- reference arm
     if args.impl == 'reference':
@@ -733,7 +768,7 @@ def main():
         print(json.dumps(dict(impl='reference', metric=METRIC, value=round(v, 1), unit='ms', n_gpus=args.gpus, steps=args.steps,
                               warmup=args.warmup, ms_per_step=round(v, 1), higher_is_better=False, scaling='strong',
                               vs_baseline=None, dtype='f32', data='synthetic', config=config,
-                              cpu_baseline=dict(value=round(v, 1), unit='ms', cores=threads, kind='port', sample=sample, split_ms=detail,
+                              cpu_baseline=dict(value=round(v, 1), unit='ms', cores=threads, kind=cpu_kind(), kind_detail=CPU_KIND_DETAIL[cpu_kind()], sample=sample, split_ms=detail,
                                                 reference_checkout_present=os.path.isdir('/root/reference')),
                               e2e=dict(value=round(v, 1), unit='ms', h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
         return 0
@@ -837,7 +872,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, detail, n_s = cpu_round_ms(cfg, CPU_SAMPLE_ROWS, threads, repeats=2)
-        cpu_baseline = dict(value=round(v, 1), unit='ms', cores=threads, kind='port', split_ms=detail,
+        cpu_baseline = dict(value=round(v, 1), unit='ms', cores=threads, kind=cpu_kind(), kind_detail=CPU_KIND_DETAIL[cpu_kind()], split_ms=detail,
                             reference_checkout_present=os.path.isdir('/root/reference'),
                             sample=f'{n_s} of {cfg.n} rows (all {cfg.k} centroids, all {cfg.v} names), time scaled linearly in rows')
 

@@ -25,7 +25,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d['n_gpus'] == 1 and d['steps'] == 1 and d['warmup'] == 0 and d['data'] == 'synthetic' and d['scaling'] == 'strong'
     assert d['config']['workload'].startswith('C2: 127000x768') and 'model' not in d['config']
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and '512 of 127000 rows' in cb['sample']
+    # "reference" where the checkout is importable (the E-step then runs the reference's own pairwise_distance), "port" elsewhere
+    want_kind = 'reference' if os.path.isdir('/root/reference/local_utils') else 'port'
+    assert cb['kind'] == want_kind and cb['kind_detail'] and cb['cores'] >= 1 and cb['value'] == d['value'] and '512 of 127000 rows' in cb['sample']
+    r2 = _run({'SCD_REFERENCE_DIR': '/nonexistent'})
+    assert json.loads(r2.stdout.strip())['cpu_baseline']['kind'] == 'port'
     assert d['e2e'] == {'value': d['value'], 'unit': 'ms', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
 
 
