@@ -657,7 +657,8 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 // or the all-gathered lists of several vocabulary shards: IdxT=long long, PRESCALED values) into the
 // final sorted top-k: value descending, ties -> lower index.  Also finishes the optional softmax:
 //   p_j = exp(scale * (v_j - M)) / sum_parts s_p * exp(scale * (m_p - M)).
-template <typename IdxT, bool PRESCALED>
+template <typename IdxT, bool PRESCALED, int KMAX, bool FULL>   // KMAX >= max(kt_in, k_out), FULL: k_out == KMAX - the lists live in
+                                                                 // registers and every subscript is a compile-time constant
 __global__ void topk_merge_kernel(const float* __restrict__ part_val, const IdxT* __restrict__ part_idx,
                                   const float* __restrict__ part_max, const float* __restrict__ part_sum,
                                   int parts, long long n_rows, int kt_in, int k_out, float scale, int want_softmax,
@@ -668,27 +669,45 @@ __global__ void topk_merge_kernel(const float* __restrict__ part_val, const IdxT
   // lists of one launch of name_topk_kernel: a row block has pieces(rb) pieces x 2 column halves (work.P > 0);
   // all-gathered vocabulary shards: `parts` lists for every row
   if (work.P > 0) parts = work.pieces((int)(row / (2 * kBlockM))) * kEpiHalves;
-  float bv[8]; long long bi[8];
+  float bv[KMAX]; long long bi[KMAX];                    // (value descending, index ascending); entries >= k_out stay empty
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { bv[j] = -INFINITY; bi[j] = -1; }
+  for (int j = 0; j < KMAX; ++j) { bv[j] = -INFINITY; bi[j] = -1; }
+  auto before = [](float xa, long long ia, float xb, long long ib) { return ib < 0 || xa > xb || (xa == xb && ia < ib); };
   float M = -INFINITY;
   for (int q = 0; q < parts; ++q) {
     const long long slot = (long long)q * n_rows + row;
-    if ((long long)part_idx[slot * kt_in] < 0) continue;       // this row has nothing in part q
-    for (int j = 0; j < kt_in; ++j) {
-      const float x = part_val[slot * kt_in + j];
-      const long long id = (long long)part_idx[slot * kt_in + j];
-      if (id < 0) continue;
-      int pos = k_out;                       // insert keeping (value desc, index asc)
-      for (int s = k_out - 1; s >= 0; --s) {
-        if (bi[s] < 0 || x > bv[s] || (x == bv[s] && id < bi[s])) pos = s; else break;
+    // the whole list of part q is loaded at once (independent loads).  Round 2a's version indexed its lists with runtime
+    // subscripts: they lived in local memory and the shifting loop was 55 % of the kernel's instructions (31 us at C2).
+    float xv[KMAX]; long long xi[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      xv[j] = j < kt_in ? part_val[slot * kt_in + j] : -INFINITY;
+      xi[j] = j < kt_in ? (long long)part_idx[slot * kt_in + j] : -1;
+    }
+    if (xi[0] < 0) continue;                             // this row has nothing in part q
+    if (part_max) M = fmaxf(M, part_max[slot]);
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      if (xi[j] < 0) continue;
+      float lv = bv[KMAX - 1]; long long li = bi[KMAX - 1];      // the last element currently kept (position k_out - 1)
+      if (!FULL) {
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t) if (t == k_out - 1) { lv = bv[t]; li = bi[t]; }
       }
-      if (pos < k_out) {
-        for (int s = k_out - 1; s > pos; --s) { bv[s] = bv[s - 1]; bi[s] = bi[s - 1]; }
-        bv[pos] = x; bi[pos] = id;
+      if (!before(xv[j], xi[j], lv, li)) continue;
+      if (FULL) { bv[KMAX - 1] = xv[j]; bi[KMAX - 1] = xi[j]; }
+      else {
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t) if (t == k_out - 1) { bv[t] = xv[j]; bi[t] = xi[j]; }
+      }
+#pragma unroll
+      for (int t = KMAX - 1; t > 0; --t) {
+        if ((FULL || t < k_out) && before(bv[t], bi[t], bv[t - 1], bi[t - 1])) {
+          const float tv = bv[t]; bv[t] = bv[t - 1]; bv[t - 1] = tv;
+          const long long ti = bi[t]; bi[t] = bi[t - 1]; bi[t - 1] = ti;
+        }
       }
     }
-    if (part_max) M = fmaxf(M, part_max[slot]);
   }
   float S = 0.f;
   if (part_max) {
@@ -700,7 +719,9 @@ __global__ void topk_merge_kernel(const float* __restrict__ part_val, const IdxT
     }
     if (out_max) { out_max[row] = M; out_sum[row] = S; }
   }
-  for (int j = 0; j < k_out; ++j) {
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    if (j >= k_out) continue;
     float val = PRESCALED ? bv[j] : bv[j] * scale;
     if (want_softmax) val = (PRESCALED ? expf(bv[j] - scale * M) : expf(scale * (bv[j] - M))) / S;
     out_val[row * k_out + j] = val;

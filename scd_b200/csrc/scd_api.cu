@@ -681,10 +681,18 @@ int scd_name_topk(const scd_bf16_t* X, int64_t N, int D, const scd_bf16_t* Wt, i
   if (e) return e;
 
   const bool stats = want_softmax || row_max || row_sumexp;
-  scd::topk_merge_kernel<int, false><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(
-      p.part_val, p.part_idx, stats ? p.part_max : nullptr, stats ? p.part_sum : nullptr, pl.n_slots * scd::kEpiHalves, N, pl.kt, k, scale,
-      want_softmax ? 1 : 0, idx_offset, vals, reinterpret_cast<long long*>(idx), row_max, row_sumexp,
-      scd::NameWork{pl.work_total, pl.tiles_total, pl.n_pairs});
+  {
+    const dim3 mg((unsigned)((N + 127) / 128));
+    const scd::NameWork mw_{pl.work_total, pl.tiles_total, pl.n_pairs};
+#define SCD_MERGE(KM, FULL)                                                                                                   \
+    scd::topk_merge_kernel<int, false, KM, FULL><<<mg, 128, 0, st>>>(p.part_val, p.part_idx, stats ? p.part_max : nullptr,          \
+        stats ? p.part_sum : nullptr, pl.n_slots * scd::kEpiHalves, N, pl.kt, k, scale, want_softmax ? 1 : 0, idx_offset, vals, \
+        reinterpret_cast<long long*>(idx), row_max, row_sumexp, mw_)
+    if (pl.kt == 1) SCD_MERGE(1, true);
+    else if (pl.kt == 5) { if (k == 5) SCD_MERGE(5, true); else SCD_MERGE(5, false); }
+    else { if (k == 8) SCD_MERGE(8, true); else SCD_MERGE(8, false); }
+#undef SCD_MERGE
+  }
   SCD_LAUNCH_CHECK("topk_merge_kernel");
   return 0;
 }
@@ -695,10 +703,18 @@ int scd_topk_merge(const float* part_vals, const int64_t* part_idx, const float*
   if (N == 0) return 0;
   if (!part_vals || !part_idx || !vals || !idx) return fail("scd_topk_merge: null pointer");
   if (want_softmax && (!part_max || !part_sum)) return fail("scd_topk_merge: softmax needs per-part row_max / row_sumexp");
-  scd::topk_merge_kernel<long long, true><<<(unsigned)((N + 127) / 128), 128, 0, as_stream(stream)>>>(
-      part_vals, reinterpret_cast<const long long*>(part_idx), want_softmax ? part_max : nullptr, want_softmax ? part_sum : nullptr,
-      parts, N, k, k, scale, want_softmax ? 1 : 0, 0, vals, reinterpret_cast<long long*>(idx), nullptr, nullptr,
-      scd::NameWork{0, 1, 0});
+  {
+    const dim3 mg((unsigned)((N + 127) / 128));
+    cudaStream_t st = as_stream(stream);
+#define SCD_MERGE(KM, FULL)                                                                                                   \
+    scd::topk_merge_kernel<long long, true, KM, FULL><<<mg, 128, 0, st>>>(part_vals, reinterpret_cast<const long long*>(part_idx),  \
+        want_softmax ? part_max : nullptr, want_softmax ? part_sum : nullptr, parts, N, k, k, scale, want_softmax ? 1 : 0, 0,  \
+        vals, reinterpret_cast<long long*>(idx), nullptr, nullptr, scd::NameWork{0, 1, 0})
+    if (k == 1) SCD_MERGE(1, true);
+    else if (k <= 5) { if (k == 5) SCD_MERGE(5, true); else SCD_MERGE(5, false); }
+    else { if (k == 8) SCD_MERGE(8, true); else SCD_MERGE(8, false); }
+#undef SCD_MERGE
+  }
   SCD_LAUNCH_CHECK("topk_merge_kernel<shards>");
   return 0;
 }
