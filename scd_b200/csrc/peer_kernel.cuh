@@ -139,26 +139,50 @@ finalize_centers_peer_kernel(const PeerPtrs pp, int channel, size_t buf_word_off
 
   const int k = blockIdx.x;
   const int G = pp.world;
-  int cnt_i = 0;
-  for (int r = 0; r < G; ++r)
-    cnt_i += ld_peer_i1(reinterpret_cast<const int*>(reinterpret_cast<const float*>(pp.buf[r]) + buf_word_offset + (size_t)K * D) + k);
-  const float cnt = (float)cnt_i;
-  if (threadIdx.x == 0 && counts_out) counts_out[k] = cnt;
-  if (k == 0 && threadIdx.x == 0 && inertia_out) {
-    double t = 0.0;
-    for (int r = 0; r < G; ++r)
-      t += ld_peer_d1(reinterpret_cast<const double*>(reinterpret_cast<const float*>(pp.buf[r]) + buf_word_offset + peer_mstep_inertia_word(K, D)));
-    *inertia_out = t;
-  }
+  // Every peer load of the block is issued before the first one is consumed: a load over NVLink takes ~2 us, and the first
+  // version's `for r: s += load(r)` paid that G times in a row (47 us for the reduce + divide at 8 ranks, 11 us at one).
+  __shared__ int sh_cnt[kPeerMaxWorld];
+  __shared__ double sh_inertia[kPeerMaxWorld];
+  if ((int)threadIdx.x < G)
+    sh_cnt[threadIdx.x] = ld_peer_i1(reinterpret_cast<const int*>(reinterpret_cast<const float*>(pp.buf[threadIdx.x]) + buf_word_offset + (size_t)K * D) + k);
+  if (k == 0 && inertia_out && threadIdx.x >= 32 && (int)threadIdx.x < 32 + G)
+    sh_inertia[threadIdx.x - 32] = ld_peer_d1(reinterpret_cast<const double*>(reinterpret_cast<const float*>(pp.buf[threadIdx.x - 32]) +
+                                                                                 buf_word_offset + peer_mstep_inertia_word(K, D)));
   float part = 0.f, npart = 0.f;
   const bool vec = (D & 3) == 0;
-  for (int d4 = threadIdx.x * 4; d4 < D; d4 += blockDim.x * 4) {
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
+  float cnt = 0.f;
+  bool have_cnt = false;
+  for (int d4 = threadIdx.x * 4; d4 < D || !have_cnt; d4 += blockDim.x * 4) {
+    float4 v[kPeerMaxWorld];
     const int nd = min(4, D - d4);
-    for (int r = 0; r < G; ++r) {                      // fixed rank order: identical bits on every rank
-      const float* src = reinterpret_cast<const float*>(pp.buf[r]) + buf_word_offset + (size_t)k * D + d4;
-      if (vec) { const float4 v = ld_peer_f4(src); s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w; }
-      else for (int q = 0; q < nd; ++q) s[q] += ld_peer_f1(src + q);
+    if (d4 < D) {
+#pragma unroll
+      for (int r = 0; r < kPeerMaxWorld; ++r) {          // fixed rank order below: identical bits on every rank
+        if (r >= G) continue;
+        const float* src = reinterpret_cast<const float*>(pp.buf[r]) + buf_word_offset + (size_t)k * D + d4;
+        if (vec) v[r] = ld_peer_f4(src);
+        else { v[r] = make_float4(0.f, 0.f, 0.f, 0.f); v[r].x = ld_peer_f1(src); if (nd > 1) v[r].y = ld_peer_f1(src + 1); if (nd > 2) v[r].z = ld_peer_f1(src + 2); if (nd > 3) v[r].w = ld_peer_f1(src + 3); }
+      }
+    }
+    if (!have_cnt) {                                     // first trip: the counts (and the inertia) have landed in shared memory
+      __syncthreads();
+      int cnt_i = 0;
+      for (int r = 0; r < G; ++r) cnt_i += sh_cnt[r];
+      cnt = (float)cnt_i;
+      have_cnt = true;
+      if (threadIdx.x == 0 && counts_out) counts_out[k] = cnt;
+      if (k == 0 && threadIdx.x == 0 && inertia_out) {
+        double t = 0.0;
+        for (int r = 0; r < G; ++r) t += sh_inertia[r];
+        *inertia_out = t;
+      }
+    }
+    if (d4 >= D) break;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < kPeerMaxWorld; ++r) {
+      if (r >= G) continue;
+      s[0] += v[r].x; s[1] += v[r].y; s[2] += v[r].z; s[3] += v[r].w;
     }
     for (int q = 0; q < nd; ++q) {
       const int d = d4 + q;

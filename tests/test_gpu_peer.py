@@ -75,6 +75,18 @@ def _worker(rank, world, port, errq):
         dist.all_gather(both, sh.cluster_centers_.contiguous())
         assert torch.equal(both[0].view(torch.int32), both[1].view(torch.int32))
 
+        # ---- a width that is not a multiple of 4 (scalar peer loads, fp32 direct-form E-step)
+        g6 = torch.Generator().manual_seed(3)
+        X6 = torch.randn(2000, 6, generator=g6) + 3.0 * torch.randn(5, 6, generator=g6)[torch.randint(0, 5, (2000,), generator=g6)]
+        l6, h6 = sdist.shard_bounds(2000, world, rank)
+        one = kmeans.K_Means(k=5, max_iterations=8, n_init=1, init='first')
+        one.fit(X6.cuda())
+        sh = kmeans.K_Means(k=5, max_iterations=8, n_init=1, init='first', process_group=group)
+        sh.fit(X6[l6:h6].cuda())
+        assert sh._peer_exchange(5, 6, torch.device('cuda', rank)) is not None
+        assert torch.allclose(sh.cluster_centers_, one.cluster_centers_, atol=1e-4, rtol=1e-4)
+        assert (sh.labels_ == one.labels_[l6:h6]).float().mean().item() > 0.995
+
         # ---- the row-sharded round: records pushed over peer memory, vote == the single-rank vote, several rounds
         # back to back (double-buffered record arrays, device-side epochs)
         C0 = data['C0'].cuda()
