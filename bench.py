@@ -342,8 +342,19 @@ class Round:
         self.px = None
         if world > 1 and exchange == 'peer':
             from scd_b200 import peer
-            self.px = peer.PeerExchange(group, cfg.k, d, n_total=cfg.n, k_used=TOPK, device=dev)
+            import torch.distributed as dist
+            ok = 1
+            try:
+                self.px = peer.PeerExchange(group, cfg.k, d, n_total=cfg.n, k_used=TOPK, device=dev)
+            except Exception as e:                                  # symmetric memory unavailable on this box: every rank fails alike
+                sys.stderr.write(f'[bench] rank {rank}: peer-memory exchange unavailable ({e}); using the NCCL collectives\n')
+                ok = 0
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # one path for all ranks
+            if not bool(flag.item()):
+                self.px = None
             self.inertia_red = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.exchange = 'peer' if self.px is not None else ('nccl' if world > 1 else None)
         self.g_rec = sdist.RowGather(cfg.n, (1 + TOPK,), torch.int32, dev, group) if world > 1 and self.px is None else None
         self.records = None
         self.subgroup = None
@@ -796,6 +807,7 @@ def main():
     launches_per_round = rnd.launches_per_round
     phase_us = getattr(rnd, 'phase_us', None)
     fused_flag = rnd.fused_em
+    exchange_used = rnd.exchange
     rnd.drop_graphs()
     parity = parity_block(rnd, host, world, group)
 
@@ -898,7 +910,7 @@ def main():
                     data='synthetic', config=config, clocks=clocks, e2e=e2e, gpu_launches=launches_per_round * args.steps,
                     launch_mode='cuda-graph replay' if graphed else 'eager',
                     roofline=roofline, cpu_baseline=cpu_baseline, torch_cuda_baseline=torch_base,
-                    kmeans_pass='E-step + M-step sums fused in one pass over X' if fused_flag else 'E-step, label sort, segment sum: two passes over X',
+                    exchange=exchange_used, kmeans_pass='E-step + M-step sums fused in one pass over X' if fused_flag else 'E-step, label sort, segment sum: two passes over X',
                     split=dict(naming_ms=round(name_ms, 4), rest_ms=round(ms_per_step - name_ms, 4), phases_us_rank0=phase_us),
                     parity=parity, sustained=sustained, **extra)
         real_stdout.write(json.dumps(line) + '\n')

@@ -382,12 +382,17 @@ name_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               at[kk] = tmem_base + a_tmem_col(a_in_tmem ? kb : 0, kk);
               asm volatile("" : "+l"(bd[kk]), "+l"(ad[kk]), "+r"(at[kk]));
             }
-            // Accumulator buffer free?  Waited for ahead of the token - except when a tile is a single k-block (D <= 64):
-            // an issuer then sits three tiles ahead of the one it issued last, the release it needs (tile - 2) can
-            // still have the previous release (tile - 4) pending, and a parity wait cannot tell those two phases apart
-            // (it returned at once, the MMAs overwrote a buffer the epilogue was reading, and the pair deadlocked).
-            // After the token every earlier tile has been issued, so tile - 4 has certainly been released.
-            const bool te_after_token = nkb == 1;
+            // Accumulator buffer free / rows of the item loaded?  Waited for ahead of the token - except when a tile has fewer
+            // k-blocks than there are issuers (D <= 128).  A parity wait is only sound if the waiter cannot be more than one
+            // phase away from the one it asks for.  With one k-block per tile an issuer sits three tiles ahead of the one it
+            // issued last: the release it needs (tile - 2) can still have the previous release (tile - 4) pending, the wait
+            // returned at once, the MMAs overwrote a buffer the epilogue was reading, and the pair deadlocked (round 1).
+            // With two k-blocks per tile and the ONE-TILE work items the linear partition of round 2 produces at range ends,
+            // an issuer meets k-block kb of an item only every third item: its early wait on a_full(kb) could alias with the
+            // fill before last and the MMAs read rows that were still being written (tools/naming_stress.py: 46 wrong
+            // indices in one launch of 19000 x 5000 x 128 out of ~10^4).  After the token every earlier k-block has been
+            // issued by a warp that waited for its own fill / release, so the barrier is at most one phase behind.
+            const bool te_after_token = nkb < kNumIssuers;
             if (kb == 0 && !te_after_token) { const long long c0 = prof ? clock64() : 0;
               ptx::mbar_wait(tmem_empty_bar(buf), ((tile_no >> 1) & 1u) ^ 1u, 300 + buf);
               if (prof) pf_te += clock64() - c0; }

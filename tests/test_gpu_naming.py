@@ -216,3 +216,28 @@ def test_several_row_blocks_per_cta_pair_at_narrow_widths(n, v, d, k):
         vals, idx, _, _ = naming.name_topk_raw(X.cuda(), vocab, k, False)
     rows = torch.randperm(n, generator=g)[:1500]
     _check_topk(vals[rows.cuda()], idx[rows.cuda()], X[rows].float(), W.float().t().contiguous(), k, 'ptsup', LOGIT_ATOL)
+
+
+@pytest.mark.parametrize('n,v,d,k', [(19000, 5000, 128, 1), (19000, 5000, 128, 5), (19000, 5000, 64, 5), (30000, 3000, 192, 5)])
+def test_one_tile_work_items_at_narrow_widths_are_reproducible(n, v, d, k):
+    """Regression (found by tools/naming_stress.py in round 2): the linear work partition leaves ONE-tile work items at the
+    ends of a pair's range; with two k-blocks per tile (D = 128) an MMA issuer then meets a given k-block of an item only
+    every third item, its early parity wait on the rows' barrier aliased with the fill before last, and about one launch
+    in 10^4 scored a few rows against half-written operands.  300 back-to-back launches must equal the first bit for bit,
+    and the first must equal torch on a row sample."""
+    g = torch.Generator().manual_seed(n + v + d + k)
+    X = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1).bfloat16().cuda()
+    W = torch.nn.functional.normalize(torch.randn(v, d, generator=g), dim=1).bfloat16()
+    vocab = naming.Vocabulary.from_rows(W.cuda())
+    plan = naming.TopKPlan(n, v, k, 'cuda')
+    v0, i0, _, _ = plan.run(X, vocab, False)
+    v0, i0 = v0.clone(), i0.clone()
+    rows = torch.randperm(n, generator=g)[:1500]
+    _check_topk(v0[rows.cuda()], i0[rows.cuda()], X[rows.cuda()].float().cpu(), W.float().t().contiguous(), k, 'ptsup', LOGIT_ATOL)
+    bad = 0
+    for rep in range(30):
+        for _ in range(10):                                   # no sync inside a batch
+            plan.run(X, vocab, False)
+        torch.cuda.synchronize()
+        bad += int((plan.idx != i0).sum()) + int((plan.vals != v0).sum())
+    assert bad == 0

@@ -13,7 +13,11 @@ random.seed(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 budget_s = float(sys.argv[2]) if len(sys.argv) > 2 else 40.0
 shapes = [(127000, 21000, 768, 5, False), (20000, 21000, 768, 5, True), (5000, 3000, 768, 5, False), (40000, 11000, 64, 5, False),
           (19000, 5000, 128, 1, False), (3000, 100, 768, 1, False), (70000, 2000, 512, 8, True), (513, 257, 72, 2, False),
-          (30000, 82000, 768, 5, False)]
+          (30000, 82000, 768, 5, False),
+          # round 2, linear work partition: a row shard smaller than one wave (two long items per pair), fewer tiles than pairs
+          # (one-tile items), ranges that cut row blocks into three pieces, one row block over the whole chip
+          (15875, 21000, 768, 5, False), (600, 672, 768, 5, True), (256 * 74 + 1, 3000, 256, 5, False), (4000, 30000, 768, 8, False),
+          (200, 100000, 768, 5, False)]
 data = {}
 for (n, v, d, k, sm) in shapes:
     g = torch.Generator(device='cuda').manual_seed(n + v)
