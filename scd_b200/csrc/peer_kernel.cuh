@@ -221,17 +221,36 @@ finalize_centers_peer_kernel(const PeerPtrs pp, int channel, size_t buf_word_off
 // The all-gather of the vote records IS the store: rec[g] = [label, name_0 .. name_(k-1)] (int32) of global row
 // g = row_offset + i goes to every rank's gathered array.
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_vote_records_peer_kernel(const PeerPtrs pp, size_t buf_byte_offset, const long long* __restrict__ labels,
-                                              const long long* __restrict__ idx, int k_total, int k_used, long long n,
-                                              long long row_offset) {
+// A block packs kPackRows records into shared memory (coalesced reads of labels / indices), then streams the packed bytes
+// to every rank with 8-byte stores that are contiguous across the block (a record is (1 + k) * 4 bytes: 8-byte aligned
+// whenever k is odd, as with k = 5; otherwise 4-byte stores).  The first version stored word by word from one thread per row:
+// 48 scattered 4-byte remote stores per row at 8 ranks - 320-640 us for C5's 160 k rows per rank.
+constexpr int kPackRows = 256;
+
+__global__ void __launch_bounds__(256)
+pack_vote_records_peer_kernel(const PeerPtrs pp, size_t buf_byte_offset, const long long* __restrict__ labels,
+                              const long long* __restrict__ idx, int k_total, int k_used, long long n, long long row_offset) {
+  __shared__ __align__(16) int rec[kPackRows * 9];            // k_used <= 8
   const int w = 1 + k_used;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int v[9];                                        // k_used <= 8
-    v[0] = (int)labels[i];
-    for (int j = 0; j < k_used; ++j) v[1 + j] = (int)idx[i * k_total + j];
+  for (long long r0 = (long long)blockIdx.x * kPackRows; r0 < n; r0 += (long long)gridDim.x * kPackRows) {
+    const int rows = (int)min((long long)kPackRows, n - r0);
+    __syncthreads();                                          // the previous tile has left shared memory
+    for (int t = threadIdx.x; t < rows * w; t += blockDim.x) {
+      const int i = t / w, j = t - i * w;
+      rec[t] = j == 0 ? (int)labels[r0 + i] : (int)idx[(r0 + i) * k_total + (j - 1)];
+    }
+    __syncthreads();
+    const long long first_word = (row_offset + r0) * w;       // word offset of the tile in the gathered array
+    const int words = rows * w;
+    const bool wide = ((first_word | words) & 1) == 0 && (buf_byte_offset & 7) == 0;
     for (int r = 0; r < pp.world; ++r) {
-      int* dst = reinterpret_cast<int*>(reinterpret_cast<char*>(pp.buf[r]) + buf_byte_offset) + (row_offset + i) * w;
-      for (int j = 0; j < w; ++j) dst[j] = v[j];
+      int* dst = reinterpret_cast<int*>(reinterpret_cast<char*>(pp.buf[r]) + buf_byte_offset) + first_word;
+      if (wide) {
+        for (int t = threadIdx.x; t < words / 2; t += blockDim.x)
+          reinterpret_cast<int2*>(dst)[t] = reinterpret_cast<const int2*>(rec)[t];
+      } else {
+        for (int t = threadIdx.x; t < words; t += blockDim.x) dst[t] = rec[t];
+      }
     }
   }
 }

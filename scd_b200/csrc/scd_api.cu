@@ -835,7 +835,7 @@ int scd_pack_vote_records_peer(void* const* peer_bufs, int world, int rank, size
   if (n == 0) return 0;
   if (!labels || !topk_idx) return fail("scd_pack_vote_records_peer: null pointer");
   if (k_used > 8) return fail("scd_pack_vote_records_peer: k_used=%d unsupported (<= 8)", k_used);
-  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  const int blocks = (int)std::min<long long>((n + scd::kPackRows - 1) / scd::kPackRows, 148 * 8);
   scd::pack_vote_records_peer_kernel<<<blocks, 256, 0, as_stream(stream)>>>(pp, buf_byte_offset, reinterpret_cast<const long long*>(labels),
                                                                             reinterpret_cast<const long long*>(topk_idx), k_total, k_used, n, row_offset);
   SCD_LAUNCH_CHECK("pack_vote_records_peer_kernel");
