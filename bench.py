@@ -5,25 +5,30 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C2]
 
 * default arm: the B200 path.  `value` = ms per round of the HEADLINE config (C2, the 1-GPU configuration the metric is
-  quoted on) with all inputs resident in HBM (CUDA events, max over ranks); `e2e` = the same round through the public
-  Python API with HOST (pinned) buffers, H2D/D2H inside the timed region; `roofline` = the dominant kernel (fused
-  scoring/top-k, tensor-core bound) against MEASURED_PEAKS.json; `cpu_baseline` = the oracle (a port of the reference's
-  PyTorch path) timed on this box's host cores on a bounded row sample; `torch_cuda_baseline` = the reference's own
-  PyTorch expressions run on CUDA tensors on the same GPU (N=1 / rank 0 only).
+  quoted on) with all inputs resident in HBM (CUDA events, max over ranks, rounds replayed as CUDA graphs); `e2e` = the same
+  round through the public Python API with HOST (pinned) buffers, H2D/D2H inside the timed region; `roofline` = the dominant
+  kernel (fused scoring/top-k, tensor-core bound, timed by event nodes inside the graphs) against MEASURED_PEAKS.json;
+  `split.phases_us_rank0` = event nodes at every phase boundary of the round; `cpu_baseline` = the reference's CPU path
+  (kind "reference" where the checkout is importable, else the oracle port) on this box's host cores on a bounded row
+  sample; `torch_cuda_baseline` = the reference's own PyTorch expressions on CUDA tensors on the same GPU (N=1 only);
+  `sustained` = the same graph replayed for >= 2 s.
 * N > 1 (launched by torch.distributed.run, one rank per GPU): STRONG scaling of the same workload.  Image rows are
-  block-sharded for BOTH contractions - k-means (one packed NCCL all-reduce of [K*D sums | K counts | inertia] per
-  iteration) and naming (vocabulary replicated, no exchange) - then each rank packs [label, top-k names] int32 records,
-  ONE all-gather replicates them and the exact vote runs on every rank.  `--naming-shard vocab` switches naming to the
-  vocabulary-column-sharded scheme of BASELINE.json configs[3] (all rows x V/N columns per rank, all-gather of the
-  [N, k] lists, k-way merge kernel); `--vocab-ways G` makes it a (N/G) x G rows x vocabulary process grid.
+  block-sharded for BOTH contractions - k-means and naming (vocabulary replicated, no exchange).  The two exchange steps
+  run inside the kernels over NVLink peer memory (scd_b200/peer.py): the divide kernel sums the ranks' [K*D sums | K counts
+  | inertia] blocks with peer loads, and the pack kernel stores each rank's [label, top-k names] int32 records into every
+  rank, after which the exact vote runs replicated.  `--exchange nccl` does both with NCCL launches (packed all-reduce,
+  all-gather) instead.  `--naming-shard vocab` switches naming to the vocabulary-column-sharded scheme of BASELINE.json
+  configs[3] (all rows x V/N columns per rank, all-gather of the [N, k] lists, k-way merge kernel); `--vocab-ways G` makes it
+  a (N/G) x G rows x vocabulary process grid.
 * every line also carries (unless --no-extra): `c5` - the 1.28M x 768, K=1000, V=100k stress config (configs[4]) on
   the same N GPUs, rows sharded; `c4_vocab_shard` - the V=82k sweep config (configs[3]) with the vocabulary
-  column-sharded, next to the same config row-sharded; and `parity` - sha1 hashes of labels / top-k indices / voted
-  names of one round from the initial centroids, and whether the N-rank result equals a 1-rank recomputation of the
-  whole workload on rank 0 (`equals_n1`).
-* --impl reference: the reference's own CPU implementation of the path (the oracle port - the reference is
-  Python/PyTorch, there is nothing to compile into oracle/_ref) with all host threads, on a bounded sample of
-  the same workload, extrapolated linearly in rows.  Rank 0 only.
+  column-sharded, next to the same config row-sharded (`c4_rows`; `c4_grid_2d` at N >= 4); and `parity` - sha1 hashes of
+  labels / top-k indices / voted names of one round from the initial centroids, and whether the N-rank result equals a
+  1-rank recomputation of the whole workload on rank 0 (`equals_n1`).
+* --impl reference: the reference's own CPU implementation of the path (its k-means distance function imported from the
+  checkout where present, the inline script blocks restated by the oracle - the reference is Python/PyTorch, there is
+  nothing to compile into oracle/_ref) with all host threads, on a bounded sample of the same workload, extrapolated
+  linearly in rows.  Rank 0 only.
 """
 from __future__ import annotations
 
@@ -716,8 +721,8 @@ def h2d_gbs(pinned_t):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default='C2')
     ap.add_argument('--naming-shard', default='rows', choices=['rows', 'vocab'],

@@ -69,3 +69,12 @@ def _worker(rank, world, port, k, d):
 @pytest.mark.parametrize('world', [2, 3])           # 3: ragged shards (101 rows -> 34 / 34 / 33), as on 4 or 8 GPUs
 def test_packed_allreduce_and_row_gather_gloo(world):
     mp.spawn(_worker, args=(world, _free_port(), 6, 16), nprocs=world, join=True)
+
+
+def test_peer_exchange_is_off_without_nccl():
+    """The NVLink peer-memory exchange is only chosen for NCCL groups on CUDA devices: on the CPU (and for the gloo groups
+    of these tests) K_Means falls back to the packed all-reduce and `peer.available` says so."""
+    from scd_b200 import kmeans, peer
+    assert peer.available(None) is False
+    km = kmeans.K_Means(k=3, process_group=None)
+    assert km._peer_exchange(3, 8, 'cpu') is None
