@@ -690,7 +690,7 @@ def e2e_round(cfg, host, vocab, pinned, out_host):
         out_host['vals'].copy_(vals, non_blocking=True)
         out_host['idx'].copy_(idx, non_blocking=True)
     ms = kmeans._MStep(cfg.n, synth_d, cfg.k, C.device)
-    fused = False           # one-pass E+M exists (scd_estep_mstep) but its vector reductions cost more than the second pass over X
+    fused = False           # one-pass E+M (scd_estep_mstep) per panel was tried here too: 14.51 vs 14.46 ms - the last panel's slower launch eats what the shorter tail gains
     X, labels, inertia = kmeans.assign_from_host(pinned['X'], C, mstep=ms if fused else None)   # panels up, E(+M) per panel
     centers, counts, _, ms = kmeans.update_centers(X, labels, cfg.k, mstep=ms if fused else None)
     names, counts_v, distinct, rows, ovf = naming.vote_device(idx, labels if fused else None, cfg.k, TOPK, NUM_COMMON,
