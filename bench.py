@@ -446,8 +446,15 @@ class Round:
                 out = nm.vote_device(idx, self.labels, cfg.k, TOPK, NUM_COMMON, plan=self.vote_plan); launches += 3
             else:
                 out = nm.vote_device(idx, None, cfg.k, TOPK, NUM_COMMON, plan=self.vote_plan, presorted=self.mstep); launches += 1
+        elif self.px is not None and not self.fused_em:
+            # the M-step has just sorted this rank's rows by label: the sorted runs + offsets go to every rank (pack kernel =
+            # the all-gather, + flag barrier) and the vote walks them - no sort of the gathered records
+            records, seg = self.px.gather_sorted_records(self.mstep, idx, TOPK); launches += 2
+            mark(5)
+            out = nm.vote_segments(records, seg, cfg.k, NUM_COMMON, plan=self.vote_plan, n_total=cfg.n); launches += 1
+            self.records = (records, seg)
         elif self.px is not None:
-            records = self.px.gather_records(self.labels, idx, TOPK); launches += 2   # pack kernel = the all-gather, + flag barrier
+            records = self.px.gather_records(self.labels, idx, TOPK); launches += 2
             mark(5)
             out = nm.vote_records(records, cfg.k, NUM_COMMON, plan=self.vote_plan); launches += 3
             self.records = records
@@ -621,8 +628,11 @@ def parity_block(rnd, data, world, group):
     vals, idx, _ = rnd.last
     torch.cuda.synchronize()
     if world > 1:
-        rec = rnd.records                                        # gathered [N, 1 + k] records of this very round
-        labels_all, idx_all = rec[:, 0].long(), rec[:, 1:].long()
+        rec = rnd.records                                        # gathered records of this very round
+        if isinstance(rec, tuple):                               # sorted runs [global row id, names] + per-rank offsets
+            labels_all, idx_all = rnd.px.unpack_sorted(*rec)
+        else:
+            labels_all, idx_all = rec[:, 0].long(), rec[:, 1:].long()
     else:
         labels_all, idx_all = rnd.labels, idx
     out = dict(labels_sha=sha(labels_all), topk_idx_sha=sha(idx_all), voted_sha=sha(names), vote_counts_sha=sha(counts),

@@ -234,6 +234,20 @@ SCD_API int scd_pack_vote_records_peer(void* const* peer_bufs, int world, int ra
                                const int64_t* topk_idx, int k_total, int k_used, int64_t n, int64_t row_offset,
                                scd_stream_t stream);
 
+/* The same exchange without a second sort: records leave in the label-sorted order scd_mstep_sums has just produced on this
+ * rank (mstep_ws), record = [global row id = row_offset + local row, name_0 .. name_(k-1)], slot row_offset + sorted
+ * position; the rank's [K + 1] offsets go to row `rank` of the [world, K + 1] int32 table at off_byte_offset of every rank's
+ * buffer.  scd_vote_segments (after scd_peer_barrier) votes by walking the `world` sorted runs of each cluster:
+ * rec = the local gathered array [world * per, 1 + k_used], per = rows per rank block, n_total = rows of all ranks (sizes the
+ * spill tables); same outputs as scd_vote_records. */
+SCD_API int scd_pack_sorted_records_peer(void* const* peer_bufs, int world, int rank, size_t rec_byte_offset, size_t off_byte_offset,
+                                 const int64_t* topk_idx, int k_total, int k_used, int64_t n, int64_t row_offset,
+                                 const void* mstep_ws, int K, scd_stream_t stream);
+SCD_API int scd_vote_segments(const int32_t* rec, int k_used, int64_t n_total, int64_t per, int world, const int32_t* seg_offsets, int K,
+                      const int64_t* excluded /* nullable */, int n_excluded, int M, int64_t* out_names, int32_t* out_counts,
+                      int32_t* out_distinct, int32_t* out_rows, int32_t* overflow, void* spill /* nullable */, size_t spill_bytes,
+                      scd_stream_t stream);
+
 /* ---------------------------------------------------------------- evaluation either side of the path */
 
 /* gcd/project_utils/cluster_and_log_utils.py:45-49 (split_cluster_acc_v2: `for i in range(y_pred.size):

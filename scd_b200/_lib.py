@@ -51,6 +51,8 @@ SIGNATURES = {
     'scd_peer_barrier': (_int, [_vp, _int, _int, _int, _vp]),
     'scd_finalize_centers_peer': (_int, [_vp, _vp, _int, _int, _int, _sz, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _vp]),
     'scd_pack_vote_records_peer': (_int, [_vp, _int, _int, _sz, _vp, _vp, _int, _int, _i64, _i64, _vp]),
+    'scd_pack_sorted_records_peer': (_int, [_vp, _int, _int, _sz, _sz, _vp, _int, _int, _i64, _i64, _vp, _int, _vp]),
+    'scd_vote_segments': (_int, [_vp, _int, _i64, _i64, _int, _vp, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'scd_label_histogram': (_int, [_vp, _i64, _int, _vp, _vp]),
     'scd_constrained_assign': (_int, [_vp, _i64, _int, _i64, _i64, _vp, C.POINTER(_i64), C.POINTER(_i64)]),
     'scd_contingency': (_int, [_vp, _int, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -255,4 +255,43 @@ pack_vote_records_peer_kernel(const PeerPtrs pp, size_t buf_byte_offset, const l
   }
 }
 
+// The same exchange WITHOUT the second sort: the rank's records go out in the label-sorted order its M-step has just produced
+// (`order` / `offsets` of scd_mstep_sums), record = [global row id, names], together with the rank's offsets table - every rank
+// then votes by walking the `world` sorted runs of each cluster (vote_kernel<SEG>), no histogram / scan / scatter of the
+// gathered records.
+__global__ void __launch_bounds__(256)
+pack_sorted_records_peer_kernel(const PeerPtrs pp, size_t rec_byte_offset, size_t off_byte_offset, const long long* __restrict__ idx,
+                                int k_total, int k_used, long long n, long long row_offset, const int* __restrict__ order,
+                                const int* __restrict__ offsets, int K) {
+  __shared__ __align__(16) int rec[kPackRows * 9];
+  const int w = 1 + k_used;
+  if (blockIdx.x == 0) {                                    // this rank's offsets -> row `rank` of every rank's table
+    for (int r = 0; r < pp.world; ++r) {
+      int* dst = reinterpret_cast<int*>(reinterpret_cast<char*>(pp.buf[r]) + off_byte_offset) + (size_t)pp.rank * (K + 1);
+      for (int t = threadIdx.x; t <= K; t += blockDim.x) dst[t] = offsets[t];
+    }
+  }
+  for (long long p0 = (long long)blockIdx.x * kPackRows; p0 < n; p0 += (long long)gridDim.x * kPackRows) {
+    const int rows = (int)min((long long)kPackRows, n - p0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+      const int row = order[p0 + i];
+      rec[i * w] = (int)(row_offset + row);
+      for (int j = 0; j < k_used; ++j) rec[i * w + 1 + j] = (int)idx[(long long)row * k_total + j];
+    }
+    __syncthreads();
+    const long long first_word = (row_offset + p0) * w;
+    const int words = rows * w;
+    const bool wide = ((first_word | words) & 1) == 0 && (rec_byte_offset & 7) == 0;
+    for (int r = 0; r < pp.world; ++r) {
+      int* dst = reinterpret_cast<int*>(reinterpret_cast<char*>(pp.buf[r]) + rec_byte_offset) + first_word;
+      if (wide) {
+        for (int t = threadIdx.x; t < words / 2; t += blockDim.x) reinterpret_cast<int2*>(dst)[t] = reinterpret_cast<const int2*>(rec)[t];
+      } else {
+        for (int t = threadIdx.x; t < words; t += blockDim.x) dst[t] = rec[t];
+      }
+    }
+  }
+}
+
 }  // namespace scd

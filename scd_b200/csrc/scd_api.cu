@@ -224,22 +224,24 @@ int sort_rows_by_label(const LabT* labels, long long stride, int64_t N, int K, i
   return 0;
 }
 
-template <typename IdxT>
+template <typename IdxT, bool SEG = false>
 int launch_vote(const IdxT* topk_idx, long long idx_stride, int k_used, int64_t N, const int* order, const int* offsets, int K,
                        const int64_t* excluded, int n_excluded, int M, int64_t* out_names, int32_t* out_counts,
-                       int32_t* out_distinct, int32_t* overflow, void* spill, size_t spill_bytes, cudaStream_t st) {
+                       int32_t* out_distinct, int32_t* overflow, void* spill, size_t spill_bytes, cudaStream_t st,
+                       const int* seg_offsets = nullptr, int seg_world = 0, long long seg_per = 0, int32_t* out_rows = nullptr) {
   if (spill && spill_bytes < scd::vote_spill_bytes(N, k_used)) return fail("vote: spill buffer too small (%zu < %zu)", spill_bytes, scd::vote_spill_bytes(N, k_used));
   SCD_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), st));
-  static bool attr_set[kMaxDevices][2] = {};
+  static bool attr_set[kMaxDevices][3] = {};
   const int dev = current_device_slot();
-  constexpr int which = sizeof(IdxT) == 8 ? 0 : 1;
+  constexpr int which = SEG ? 2 : (sizeof(IdxT) == 8 ? 0 : 1);
   if (!attr_set[dev][which]) {
-    SCD_CUDA(cudaFuncSetAttribute(scd::vote_kernel<IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, scd::kVoteSmemBytes));
+    SCD_CUDA(cudaFuncSetAttribute(scd::vote_kernel<IdxT, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, scd::kVoteSmemBytes));
     attr_set[dev][which] = true;
   }
-  scd::vote_kernel<IdxT><<<K, scd::kVoteThreads, scd::kVoteSmemBytes, st>>>(
+  scd::vote_kernel<IdxT, SEG><<<K, scd::kVoteThreads, scd::kVoteSmemBytes, st>>>(
       topk_idx, idx_stride, k_used, order, offsets, K, reinterpret_cast<const long long*>(excluded), n_excluded, M,
-      reinterpret_cast<long long*>(out_names), out_counts, out_distinct, overflow, reinterpret_cast<int*>(spill));
+      reinterpret_cast<long long*>(out_names), out_counts, out_distinct, overflow, reinterpret_cast<int*>(spill),
+      seg_offsets, seg_world, seg_per, out_rows);
   SCD_LAUNCH_CHECK("vote_kernel");
   return 0;
 }
@@ -840,6 +842,37 @@ int scd_pack_vote_records_peer(void* const* peer_bufs, int world, int rank, size
                                                                             reinterpret_cast<const long long*>(topk_idx), k_total, k_used, n, row_offset);
   SCD_LAUNCH_CHECK("pack_vote_records_peer_kernel");
   return 0;
+}
+
+int scd_pack_sorted_records_peer(void* const* peer_bufs, int world, int rank, size_t rec_byte_offset, size_t off_byte_offset,
+                                 const int64_t* topk_idx, int k_total, int k_used, int64_t n, int64_t row_offset, const void* mstep_ws,
+                                 int K, scd_stream_t stream) {
+  if (n < 0 || row_offset < 0 || k_total <= 0 || k_used <= 0 || k_used > k_total || k_used > 8 || K <= 0)
+    return fail("scd_pack_sorted_records_peer: bad arguments");
+  if (rec_byte_offset % 4 != 0 || off_byte_offset % 4 != 0) return fail("scd_pack_sorted_records_peer: offsets must be multiples of 4 bytes");
+  if (!mstep_ws || (n > 0 && !topk_idx)) return fail("scd_pack_sorted_records_peer: null pointer");
+  scd::PeerPtrs pp;
+  if (int e = make_peer_ptrs(&pp, peer_bufs, nullptr, world, rank, "scd_pack_sorted_records_peer")) return e;
+  const SortWs w(const_cast<void*>(mstep_ws), K);           // as written by scd_mstep_sums on this rank's labels
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((n + scd::kPackRows - 1) / scd::kPackRows, 148 * 8));
+  scd::pack_sorted_records_peer_kernel<<<blocks, 256, 0, as_stream(stream)>>>(pp, rec_byte_offset, off_byte_offset,
+      reinterpret_cast<const long long*>(topk_idx), k_total, k_used, n, row_offset, w.order, w.offsets, K);
+  SCD_LAUNCH_CHECK("pack_sorted_records_peer_kernel");
+  return 0;
+}
+
+int scd_vote_segments(const int32_t* rec, int k_used, int64_t n_total, int64_t per, int world, const int32_t* seg_offsets, int K,
+                      const int64_t* excluded, int n_excluded, int M, int64_t* out_names, int32_t* out_counts,
+                      int32_t* out_distinct, int32_t* out_rows, int32_t* overflow, void* spill, size_t spill_bytes,
+                      scd_stream_t stream) {
+  if (per < 0 || world < 1 || world > scd::kVoteMaxSeg || K <= 0 || k_used <= 0 || M <= 0 || n_total < 0 || n_total > per * world)
+    return fail("scd_vote_segments: bad arguments");
+  const int64_t N = n_total;
+  if (N * (int64_t)k_used >= (1ll << 31)) return fail("scd_vote_segments: N * k_used exceeds the 31-bit position range");
+  if (!rec || !seg_offsets || !out_names || !out_counts || !out_distinct || !out_rows || !overflow) return fail("scd_vote_segments: null pointer");
+  if (n_excluded > 0 && !excluded) return fail("scd_vote_segments: excluded list is null");
+  return launch_vote<int, true>(rec, 1 + k_used, k_used, N, nullptr, nullptr, K, excluded, n_excluded, M, out_names, out_counts, out_distinct,
+                                overflow, spill, spill_bytes, as_stream(stream), seg_offsets, world, per, out_rows);
 }
 
 int scd_contingency(const void* y_pred, int pred_is_f64, const void* y_true, int true_is_f64, int64_t N, int D,

@@ -28,13 +28,21 @@ __host__ __device__ inline size_t vote_spill_bytes(long long N, int k_used) { re
 
 // Names are read through (pointer, row stride): int64 [N, k_total] top-k indices, or the name columns of the packed
 // int32 vote records [N][1 + k] of the multi-GPU path.
-template <typename IdxT>
+// SEG = true (row-sharded vote without a second sort): `topk_idx` is the gathered record array
+// [world * per][1 + k] int32 whose rank-r block holds that rank's records IN ITS OWN LABEL-SORTED ORDER,
+// record = [global row id, name_0 .. name_(k-1)], and seg_offsets [world][K + 1] are the ranks' M-step offsets: the rows of
+// cluster c are the `world` segments  r * per + [seg_offsets[r][c], seg_offsets[r][c + 1])  - "histograms add" by walking
+// sorted runs; out_rows[c] gets the cluster's row count.
+constexpr int kVoteMaxSeg = 16;
+
+template <typename IdxT, bool SEG>
 __global__ void __launch_bounds__(kVoteThreads)
 vote_kernel(const IdxT* __restrict__ topk_idx, long long idx_stride, int k_used,
             const int* __restrict__ order, const int* __restrict__ offsets, int K,
             const long long* __restrict__ excluded, int n_excluded, int M,
             long long* __restrict__ out_names, int* __restrict__ out_counts, int* __restrict__ out_distinct,
-            int* __restrict__ overflow_flag, int* __restrict__ spill) {
+            int* __restrict__ overflow_flag, int* __restrict__ spill,
+            const int* __restrict__ seg_offsets, int seg_world, long long seg_per, int* __restrict__ out_rows) {
   extern __shared__ int vote_sh[];
   int* hist = vote_sh + 3 * kVoteSlots;
   unsigned* cand = reinterpret_cast<unsigned*>(vote_sh + 3 * kVoteSlots + kVoteHistBins);
@@ -45,7 +53,27 @@ vote_kernel(const IdxT* __restrict__ topk_idx, long long idx_stride, int k_used,
   __shared__ int chosen_slot;
 
   const int c = blockIdx.x;
-  const int p0 = offsets[c], p1 = offsets[c + 1];
+  __shared__ int seg_pre[kVoteMaxSeg + 1];          // SEG: rows of the cluster before segment r
+  __shared__ long long seg_base[kVoteMaxSeg];       // SEG: record index of segment r's first row
+  __shared__ int seg_p0;
+  int p0, p1;
+  if (SEG) {
+    if (threadIdx.x == 0) {
+      int run = 0, before = 0;
+      for (int r = 0; r < seg_world; ++r) {
+        const int a = seg_offsets[(long long)r * (K + 1) + c], b = seg_offsets[(long long)r * (K + 1) + c + 1];
+        seg_pre[r] = run; seg_base[r] = (long long)r * seg_per + a;
+        run += b - a; before += a;
+      }
+      seg_pre[seg_world] = run;
+      seg_p0 = before;                               // rows of lower clusters over all ranks: this cluster's slice of the spill buffer
+      if (out_rows) out_rows[c] = run;
+    }
+    __syncthreads();
+    p0 = seg_p0; p1 = p0 + seg_pre[seg_world];
+  } else {
+    p0 = offsets[c]; p1 = offsets[c + 1];
+  }
   const long long n_entries = (long long)(p1 - p0) * k_used;
   // where the table lives: shared memory when 2 * entries slots fit (it then can never fill up), else the spill buffer
   const bool in_smem = 2 * n_entries <= kVoteSlots || spill == nullptr;
@@ -73,11 +101,28 @@ vote_kernel(const IdxT* __restrict__ topk_idx, long long idx_stride, int k_used,
     for (int u = 0; u < kVoteBatch; ++u) {
       const int e = base + u * (int)blockDim.x + (int)threadIdx.x;
       row[u] = -1;
-      if (e < n_ent) { const int r = e / k_used; jj[u] = e - r * k_used; row[u] = order[p0 + r]; }
+      if (e < n_ent) {
+        const int r = e / k_used; jj[u] = e - r * k_used;
+        if (SEG) {                                   // r-th row of the cluster -> its segment -> its record
+          int sgm = 0;
+          while (sgm + 1 < seg_world && r >= seg_pre[sgm + 1]) ++sgm;
+          const long long pos = seg_base[sgm] + (r - seg_pre[sgm]);
+          const IdxT* rp = topk_idx + pos * idx_stride;
+          row[u] = (int)rp[0];                       // global row id: first positions order the ties exactly as one rank would
+          name64[u] = (long long)rp[1 + jj[u]];
+        } else {
+          row[u] = order[p0 + r];
+        }
+      }
     }
+    if (!SEG) {
 #pragma unroll
-    for (int u = 0; u < kVoteBatch; ++u)
-      name64[u] = row[u] >= 0 ? (long long)topk_idx[(long long)row[u] * idx_stride + jj[u]] : -1;
+      for (int u = 0; u < kVoteBatch; ++u)
+        name64[u] = row[u] >= 0 ? (long long)topk_idx[(long long)row[u] * idx_stride + jj[u]] : -1;
+    } else {
+#pragma unroll
+      for (int u = 0; u < kVoteBatch; ++u) if (row[u] < 0) name64[u] = -1;
+    }
 #pragma unroll
     for (int u = 0; u < kVoteBatch; ++u) {
       if (name64[u] < 0) continue;

@@ -134,12 +134,17 @@ def grid_2d(world: int, rank: int, vocab_ways: int):
 
 
 def sharded_vote(labels_local: torch.Tensor, idx_local: torch.Tensor, top_k: int, n_clusters: int, num_common: int,
-                 gather: 'RowGather', plan=None, known_name_idx=None):
+                 gather: 'RowGather', plan=None, known_name_idx=None, presorted=None):
     """Row-sharded vote: pack this rank's records into ``gather.local`` (``RowGather(n_total, (1 + top_k,), int32)``),
     all-gather once, vote on the gathered records.  Every rank returns the full result of ``naming.vote_device``.
     ``gather`` may also be a ``peer.PeerExchange``: the records are then stored straight into every rank's gathered
     array over NVLink peer memory (no NCCL launch)."""
     from . import naming
+    if presorted is not None and hasattr(gather, 'gather_sorted_records'):
+        # the rank's rows are already sorted by label (kmeans._MStep.sums_counts has just run on `labels_local`): exchange the
+        # sorted runs + offsets and vote by walking them - no sort of the gathered records
+        records, seg = gather.gather_sorted_records(presorted, idx_local, top_k)
+        return naming.vote_segments(records, seg, n_clusters, num_common, known_name_idx=known_name_idx, plan=plan, n_total=gather.n_total)
     if hasattr(gather, 'gather_records'):          # peer.PeerExchange: the pack kernel's stores are the all-gather
         records = gather.gather_records(labels_local, idx_local, top_k)
     else:

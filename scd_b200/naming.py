@@ -321,6 +321,30 @@ def vote_records(records: torch.Tensor, n_clusters: int, num_common: int, known_
     return plan.names, plan.counts, plan.distinct, plan.rows, plan.overflow
 
 
+def vote_segments(records: torch.Tensor, seg_offsets: torch.Tensor, n_clusters: int, num_common: int, known_name_idx=None,
+                  plan: VotePlan | None = None, n_total: int | None = None):
+    """The vote over gathered SORTED-RUN records (``peer.PeerExchange.gather_sorted_records``): ``records``
+    ``[world * per, 1 + top_k]`` int32 = ``[global row id, names]`` in each rank's label-sorted order, ``seg_offsets``
+    ``[world, K + 1]`` the ranks' offsets.  No sort of the gathered rows; same outputs as ``vote_device``."""
+    world, per = int(seg_offsets.shape[0]), int(records.shape[0]) // int(seg_offsets.shape[0])
+    top_k = int(records.shape[1]) - 1
+    K, M = int(n_clusters), int(num_common)
+    n_total = world * per if n_total is None else int(n_total)
+    if plan is None:
+        plan = VotePlan(n_total, K, M, records.device, k_used=top_k)
+    elif (plan.K, plan.M) != (K, M) or plan.k_used < top_k or plan.n < n_total:
+        raise ValueError('VotePlan was built for a different shape')
+    excl = None
+    if known_name_idx is not None and len(known_name_idx):
+        excl = torch.as_tensor(np.asarray(list(known_name_idx), dtype=np.int64), device=records.device)
+    lib = _lib.load()
+    _lib.check(lib.scd_vote_segments(records.data_ptr(), top_k, n_total, per, world, seg_offsets.data_ptr(), K, _lib.ptr(excl),
+                                     0 if excl is None else int(excl.numel()), M, plan.names.data_ptr(), plan.counts.data_ptr(),
+                                     plan.distinct.data_ptr(), plan.rows.data_ptr(), plan.overflow.data_ptr(), *plan.spill_args(), _stream()),
+               'scd_vote_segments')
+    return plan.names, plan.counts, plan.distinct, plan.rows, plan.overflow
+
+
 def vote(name_idx_topk, u_preds, cluster_ids, top_k: int, num_common: int, known_name_idx=None):
     """``cluster_to_counter`` of ``main_unsup.py:575-577`` / ``main_ptsup.py:636-638``, truncated to each
     cluster's ``num_common`` most common names (all the loop ever reads: ``most_common(num_common_vote)``

@@ -57,9 +57,11 @@ class PeerExchange:
         self.per = (self.n_total + self.world - 1) // self.world if self.n_total else 0      # rows per rank (dist.shard_bounds)
         self.rec_w = 1 + self.k_used
         self.rec_bytes = _align(self.world * self.per * self.rec_w * 4) if self.n_total else 0
+        self.seg_bytes = _align(self.world * (self.k + 1) * 4) if self.n_total else 0      # [world, K + 1] offsets of the sorted runs
         self.off_mstep = flag_bytes
         self.off_rec = self.off_mstep + 2 * self.mstep_bytes
-        total = self.off_rec + 2 * self.rec_bytes
+        self.off_seg = self.off_rec + 2 * self.rec_bytes
+        total = self.off_seg + 2 * self.seg_bytes
         self.buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
         self.buf.zero_()
         self.handle = symm_mem.rendezvous(self.buf, self.group.group_name)
@@ -84,7 +86,9 @@ class PeerExchange:
             base = self.off_rec + p * self.rec_bytes
             if self.n_total:
                 rec = self.buf[base:base + self.world * self.per * self.rec_w * 4].view(torch.int32).view(self.world * self.per, self.rec_w)
-                self._records.append((rec, base))
+                sbase = self.off_seg + p * self.seg_bytes
+                seg = self.buf[sbase:sbase + self.world * (self.k + 1) * 4].view(torch.int32).view(self.world, self.k + 1)
+                self._records.append((rec, base, seg, sbase))
 
     # ------------------------------------------------------------------ M-step
     def next_mstep_block(self):
@@ -112,7 +116,7 @@ class PeerExchange:
         if not self.n_total or k_used != self.k_used:
             raise ValueError('PeerExchange was not sized for these vote records')
         lib = _lib.load()
-        rec, base = self._records[self._rec_parity]
+        rec, base = self._records[self._rec_parity][:2]
         self._rec_parity ^= 1
         n = int(labels_local.shape[0])
         st = torch.cuda.current_stream().cuda_stream
@@ -120,6 +124,36 @@ class PeerExchange:
                                                   int(idx_local.shape[1]), k_used, n, self.rank * self.per, st), 'scd_pack_vote_records_peer')
         _lib.check(lib.scd_peer_barrier(self.table, self.world, self.rank, RECORD_CHANNEL, st), 'scd_peer_barrier')
         return rec[:self.n_total]
+
+    def gather_sorted_records(self, mstep, idx_local: torch.Tensor, k_used: int):
+        """The exchange without a second sort: ``mstep`` is the ``kmeans._MStep`` whose ``sums_counts`` has just sorted this
+        rank's rows by label.  Records ``[global row id, names]`` leave in that order together with the rank's offsets;
+        returns ``(records [world * per, 1 + k] int32, offsets [world, K + 1] int32)`` for ``naming.vote_segments`` - every
+        cluster is then ``world`` sorted runs."""
+        if not self.n_total or k_used != self.k_used or mstep.k != self.k:
+            raise ValueError('PeerExchange was not sized for these vote records')
+        lib = _lib.load()
+        rec, base, seg, sbase = self._records[self._rec_parity]
+        self._rec_parity ^= 1
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.scd_pack_sorted_records_peer(self.table, self.world, self.rank, base, sbase, idx_local.data_ptr(),
+                                                    int(idx_local.shape[1]), k_used, int(idx_local.shape[0]), self.rank * self.per,
+                                                    mstep.ws.data_ptr(), self.k, st), 'scd_pack_sorted_records_peer')
+        _lib.check(lib.scd_peer_barrier(self.table, self.world, self.rank, RECORD_CHANNEL, st), 'scd_peer_barrier')
+        return rec, seg
+
+    def unpack_sorted(self, rec: torch.Tensor, seg: torch.Tensor):
+        """(labels [N_total] int64, top-k names [N_total, k] int64) in ROW order from gathered sorted-run records (tests / parity)."""
+        labels = torch.full((self.n_total,), -1, dtype=torch.int64, device=rec.device)
+        names = torch.full((self.n_total, self.k_used), -1, dtype=torch.int64, device=rec.device)
+        seg_h = seg.cpu()
+        for r in range(self.world):
+            n_r = int(seg_h[r, self.k])
+            block = rec[r * self.per:r * self.per + n_r].long()
+            lab_r = torch.repeat_interleave(torch.arange(self.k, device=rec.device), (seg_h[r, 1:] - seg_h[r, :-1]).to(rec.device))
+            labels[block[:, 0]] = lab_r
+            names[block[:, 0]] = block[:, 1:]
+        return labels, names
 
     def barrier(self, channel: int = 7):
         lib = _lib.load()

@@ -104,6 +104,24 @@ def _worker(rank, world, port, errq):
             assert torch.equal(names, names1) and torch.equal(counts, counts1) and torch.equal(distinct, distinct1) and torch.equal(rows, rows1)
             rec = px._records[px._rec_parity ^ 1][0][:cfg.n]
             assert torch.equal(rec[:, 0].long(), lab1) and torch.equal(rec[:, 1:].long(), idx1)
+        # ---- the same vote WITHOUT sorting the gathered records: each rank sends its rows in the label-sorted order of its own
+        # M-step + its offsets, every cluster is then `world` sorted runs (scd_pack_sorted_records_peer + scd_vote_segments)
+        ms = kmeans._MStep(hi - lo, 256, cfg.k, torch.device('cuda', rank))
+        for rnd in range(4):
+            ms.sums_counts(Xs, lab_s)
+            names, counts, distinct, rows, ovf = sdist.sharded_vote(lab_s, idx_s, 5, cfg.k, 20, px, presorted=ms)
+            assert int(ovf.item()) == 0
+            assert torch.equal(names, names1) and torch.equal(counts, counts1) and torch.equal(distinct, distinct1) and torch.equal(rows, rows1)
+        rec, base, seg, sbase = px._records[px._rec_parity ^ 1]
+        lab_u, idx_u = px.unpack_sorted(rec, seg)
+        assert torch.equal(lab_u, lab1) and torch.equal(idx_u, idx1)
+        # excluded names (the partially supervised driver drops the labelled classes' names, main_ptsup.py:638)
+        known = [int(x) for x in idx1[:50, 0].unique()[:7]]
+        n2, c2, d2, r2, _ = naming.vote_device(idx1, lab1, cfg.k, 5, 20, known_name_idx=known)
+        n2, c2 = n2.clone(), c2.clone()
+        ms.sums_counts(Xs, lab_s)
+        names, counts, _, _, _ = sdist.sharded_vote(lab_s, idx_s, 5, cfg.k, 20, px, presorted=ms, known_name_idx=known)
+        assert torch.equal(names, n2) and torch.equal(counts, c2)
         torch.cuda.synchronize()
         dist.barrier()
         os._exit(0)
